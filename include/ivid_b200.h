@@ -1,0 +1,151 @@
+/*
+ * ivid_b200 — C ABI of the B200-native (sm_100a) multiview RGBD diffusion sampling hot path.
+ *
+ * The reference (JeffreyXiang/ivid) has no FFI layer: its boundary for this path is the Python class surface that
+ * inference/sample.py resolves by name (sample.py:183-184,191-192,47-50).  The Python package `ivid_b200` mirrors
+ * those classes and binds the entry points below through ctypes.  Each entry point cites the
+ * reference interface it replaces.  All pointers are plain host or device pointers, sizes are explicit, no torch
+ * types cross this boundary.  Every function returns 0 on success or one of the IVID_ERR_* codes; the message is
+ * available (thread-local) from ivid_last_error().  The library never aborts.
+ *
+ * Unless stated otherwise `*_dev` pointers are device pointers on the handle's device, tensors are dense fp32 NCHW
+ * (the layout of the reference's torch tensors), and work is enqueued on `stream` (a cudaStream_t passed as void*).
+ */
+#ifndef IVID_B200_H_
+#define IVID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVID_OK 0
+#define IVID_ERR_INVALID_ARGUMENT 1 /* reference: Python `assert` (adm.py:540-549, ddpm.py:86)      -> AssertionError      */
+#define IVID_ERR_NOT_IMPLEMENTED 2  /* reference: NotImplementedError (frameworks/utils.py:37)      -> NotImplementedError */
+#define IVID_ERR_CUDA 3             /* CUDA runtime / driver failure                                  -> RuntimeError        */
+#define IVID_ERR_STATE 4            /* call order violation (e.g. forward before finalize)            -> RuntimeError        */
+
+typedef struct ivid_unet ivid_unet_t;
+typedef struct ivid_sampler ivid_sampler_t;
+
+const char* ivid_last_error(void);
+int ivid_version(void);
+/* Number of SMs / compute capability of `device` (diagnostics; fails without a GPU). */
+int ivid_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ADM UNet backbone  — replaces diffusion.backbones.AdmUnet2d (reference diffusion/backbones/adm.py:289-566)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* AdmUnet2d.__init__ (adm.py:318-337).  `cfg_json` is the "backbone.args" object of a reference config file
+ * (configs/(name).json), passed through unchanged.  No GPU work happens here (usable on a CPU-only host). */
+int ivid_unet_create(const char* cfg_json, ivid_unet_t** out);
+int ivid_unet_destroy(ivid_unet_t* h);
+
+/* state_dict schema (adm.py:357-366,367-487; the 494-key contract of SURVEY.md §8b): enumerate names/shapes. */
+int ivid_unet_num_params(const ivid_unet_t* h, int* count);
+int ivid_unet_param_info(const ivid_unet_t* h, int index, const char** name, int64_t shape[4], int* ndim,
+                         int* is_buffer);
+/* load_state_dict (sample.py:187): copy one fp32 host tensor in reference layout ([Cout,Cin,kh,kw], [O,I], ...). */
+int ivid_unet_set_param(ivid_unet_t* h, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* .cuda() : pack all parameters (fp16 K-major GEMM operands, fp32 norms/embeddings) into one device arena. */
+int ivid_unet_finalize(ivid_unet_t* h, int device);
+/* Device arena (for the NCCL weight broadcast at init, sample.py:186-195 loads per rank instead). */
+int ivid_unet_weight_arena(const ivid_unet_t* h, void** dev_ptr, uint64_t* bytes);
+
+/* AdmUnet2d.forward(x, times, classes) (adm.py:526-566).
+ *   x_dev       fp32 [Nx, in_channels, H, W]; sample n of the batch reads x[n % Nx] (Nx == N for the plain call)
+ *   t_dev       int64 [N]  (diffusion step minus 1, as the reference passes it)
+ *   classes_dev int64 [N] or NULL; -1 selects the null class (adm.py:551-553)
+ *   eps_dev     fp32 [N, out_channels, H, W] */
+int ivid_unet_forward(ivid_unet_t* h, const float* x_dev, int Nx, const int64_t* t_dev, const int64_t* classes_dev,
+                      float* eps_dev, int N, void* stream);
+
+/* Conditional inputs assembled on the fly (never materialised in fp32):
+ *   kind 1: InpaintCFG.make_cond_inputs (frameworks/inpaint_cfg.py:24-49): cat[x, mask_rgb, y_rgb*m_rgb+z*(1-m_rgb),
+ *           y_d*m+z*(1-m), m];  noise_dev = injected z [Nx,4,H,W] or NULL (in-kernel Philox(seed, stream)).
+ *   kind 2: SuperResCFG.make_cond_inputs (frameworks/sr_cfg.py:23-36): cat[x, bilinear_up2(y)], y is [Nx,4,H/2,W/2]. */
+typedef struct {
+  int kind;              /* 0 none, 1 inpaint, 2 super-resolution */
+  const float* y_dev;
+  const float* mask_dev;
+  const float* mask_rgb_dev;
+  const float* noise_dev;
+  uint64_t seed;
+  uint32_t stream_id;
+} ivid_cond_t;
+int ivid_unet_forward_cond(ivid_unet_t* h, const float* x_dev, int Nx, const ivid_cond_t* cond, const int64_t* t_dev,
+                           const int64_t* classes_dev, float* eps_dev, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Samplers — replace diffusion.samplers.DdpmSampler / DdimSampler (samplers/ddpm.py:12-187, samplers/ddim.py:12-165)
+ * together with the framework's model_inference (classifier_free_guidance.py:23-42, inpaint_cfg.py:61-83,
+ * sr_cfg.py:39-60).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* DdpmSampler/DdimSampler.__init__ (ddpm.py:20-41, ddim.py:19-31): derive the float64 tables from framework.betas. */
+int ivid_sampler_create(const double* betas, int timesteps, ivid_sampler_t** out);
+int ivid_sampler_destroy(ivid_sampler_t* s);
+/* Known-answer access to the float64 tables (which: 0 alphas_cumprod, 1 alphas_cumprod_prev, 2 sqrt_recip_acp,
+ * 3 sqrt_recipm1_acp, 4 posterior_variance, 5 posterior_log_variance_clipped, 6 posterior_mean_coef1, 7 coef2). */
+int ivid_sampler_table(const ivid_sampler_t* s, int which, double* out, int count);
+
+typedef struct {
+  int kind;                 /* 0 = DDPM ancestral (ddpm.py:111-131), 1 = DDIM (ddim.py:48-103) */
+  int use_cfg;              /* 1: (1+strength)*eps(c) - strength*eps(null), both halves in ONE batch-2N forward */
+  float strength;
+  int clip_denoised;
+  float eta;
+  const int64_t* classes_dev;   /* [N] or NULL */
+  ivid_cond_t cond;             /* conditional-model inputs (kind 0 for the unconditional model) */
+  /* multiview guidance of DdimSampler.sample_once (ddim.py:86-95); NULL pointers disable a term */
+  const float* replace_rgb_dev;        /* [N,3,H,W] */
+  const float* replace_rgb_mask_dev;   /* [N,1,H,W] */
+  double replace_rgb_weight;
+  const float* replace_depth_dev;      /* [N,1,H,W] */
+  const float* replace_depth_mask_dev; /* [N,1,H,W] */
+  double replace_depth_weight;
+  const float* constrain_depth_dev;    /* [N,1,H,W] convex hull depth */
+  double constrain_depth_weight;
+  /* RNG: injected noise (parity tests) or in-kernel Philox4x32-10 keyed by (seed, step) */
+  const float* step_noise_dev;         /* [N,C,H,W] noise of THIS step (ivid_sampler_step) or NULL */
+  uint64_t seed;
+} ivid_step_args_t;
+
+/* sample_once: x_prev = f(x_t, t[, t_prev]).  `t` follows the reference's convention of each sampler:
+ * DDPM: t in [0,T) is the step minus 1 (ddpm.py:118); DDIM: t in [1,T] actual step, t_prev in [0,T) (ddim.py:66-67).
+ * pred_x0_dev may be NULL. */
+int ivid_sampler_step(ivid_sampler_t* s, ivid_unet_t* unet, const float* x_t_dev, float* x_prev_dev,
+                      float* pred_x0_dev, int N, int t, int t_prev, const ivid_step_args_t* args, void* stream);
+
+/* sample: the whole reverse process on device (ddpm.py:134-187, ddim.py:106-165); x_inout_dev holds x_T on entry
+ * and the samples on return.  `steps` = DDIM step count (ignored for DDPM, which runs all T).  Optional
+ * noise_all_dev [steps][N,C,H,W] / cond_noise_all_dev [steps][N,4,H,W] inject the per-step draws; traj_x0_dev /
+ * traj_xt_dev ([steps][N,C,H,W]) receive pred_x_0 / pred_x_t of every step when non-NULL (the reference always keeps
+ * them: ddpm.py:183-184). */
+int ivid_sampler_run(ivid_sampler_t* s, ivid_unet_t* unet, float* x_inout_dev, int N, int steps,
+                     const ivid_step_args_t* args, const float* noise_all_dev, const float* cond_noise_all_dev,
+                     float* traj_x0_dev, float* traj_xt_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Operator-level entry points (unit parity tests, profiling): the kernels the UNet is assembled from.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* nn.Conv2d 3x3 pad 1 / 1x1 as tcgen05 implicit GEMM.  act_dev fp16 NHWC [N,H,W,Cin] (Cin % 64 == 0); w_host fp32
+ * [Cout,Cin,k,k] reference layout; optional 1x1 skip over act2_dev [N,H,W,Cin2] with w2_host [Cout,Cin2,1,1];
+ * optional fp32 NHWC residual; out fp32 NHWC [N,H,W,Cout] (out_fp16 = 1: fp16). */
+int ivid_op_conv2d(const void* act_dev, int N, int H, int W, int Cin, const float* w_host, const float* bias_host,
+                   int Cout, int ksize, const void* act2_dev, int Cin2, const float* w2_host, const float* bias2_host,
+                   const float* residual_dev, void* out_dev, int out_fp16, void* stream);
+/* GroupNorm32 (+FiLM) (+SiLU) (+2x up / 2x2 avg-pool) over a virtual concat of two fp32 NHWC tensors -> fp16 NHWC. */
+int ivid_op_group_norm(const float* x0_dev, int C0, const float* x1_dev, int C1, int N, int H, int W, int groups,
+                       float eps, const float* gamma_host, const float* beta_host, const float* film_dev /*[N,2C]*/,
+                       int silu, int mode, void* out_fp16_dev, void* stream);
+/* QKVAttention (adm.py:233-253): qkv fp16 [N,T,3C] (legacy head-major q|k|v order) -> fp16 [N,T,C]. */
+int ivid_op_attention(const void* qkv_dev, int N, int T, int C, void* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVID_B200_H_ */

@@ -1,0 +1,201 @@
+// Fused QKV self-attention core (FlashAttention-style, no T x T matrix in HBM) on tcgen05 / TMEM.
+//   reference: QKVAttention.forward adm.py:233-253 — per (sample, head): softmax_fp32((q*d^-1/4)^T (k*d^-1/4)) v,
+//   legacy channel order [head][q|k|v][64] of the qkv projection (adm.py:246), head dim 64.
+//
+// Input : qkv  fp16 [N][T][3C]  (NHWC output of the qkv 1x1 GEMM); head h owns channels [192h, 192h+192) = q|k|v.
+// Output: o    fp16 [N][T][C]   channel = 64*h + d   (== reshape(bs, -1, length) of the reference).
+//
+// One CTA per (sample, head, 128-query tile).  warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+// warps2-5 = softmax / output (one thread per query row).  S = Q K^T accumulates in TMEM (fp32), the un-normalised
+// probabilities P are written back to TMEM as packed fp16 and consumed as the A operand of the P V product
+// (tcgen05.mma with A in TMEM, V in shared memory as an MN-major operand); the running output is rescaled in registers
+// (online softmax).  (q*s)(k*s) with s = 64^-1/4 is evaluated as (q.k) * 0.125 — an exact power of two.
+#pragma once
+#include "common.cuh"
+
+namespace ivid {
+
+struct AttnParams {
+  int N, T, C, heads;
+  int q_tiles;        // ceil(T / 128)
+  __half* out;        // [N][T][C]
+};
+
+template <int KV>
+struct AttnCfg {
+  static constexpr int Q_BYTES = 128 * 64 * 2;
+  static constexpr int KV_BYTES = KV * 64 * 2;
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int TMEM_COLS = 256;     // S [0,KV) | P [128,128+KV/2) | O [192,256)
+  static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
+  static constexpr int THREADS = 192;
+};
+
+template <int KV>
+__global__ void __launch_bounds__(192, 2)
+attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
+                 const AttnParams p) {
+  using Cfg = AttnCfg<KV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + Cfg::Q_BYTES;                       // stage s: K at sKV + s*2*KV_BYTES, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::STAGES * 2 * Cfg::KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.q_tiles;
+  const int head = (blockIdx.x / p.q_tiles) % p.heads;
+  const int n = blockIdx.x / (p.q_tiles * p.heads);
+  const int nkv = (p.T + KV - 1) / KV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);      // one arrive per softmax warp
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+    tma_load_3d(&mapQ, q_full, sQ, head * 192, qt * 128, n);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&kv_empty[st], ph ^ 1);
+      uint8_t* sk = sKV + st * 2 * Cfg::KV_BYTES;
+      mbar_arrive_expect_tx(&kv_full[st], 2 * Cfg::KV_BYTES);
+      tma_load_3d(&mapKV, &kv_full[st], sk, head * 192 + 64, j * KV, n);
+      tma_load_3d(&mapKV, &kv_full[st], sk + Cfg::KV_BYTES, head * 192 + 128, j * KV, n);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc_s = make_idesc_f16(128, KV, false, false, false);   // S[128,KV] = Q[128,64] K[KV,64]^T
+    constexpr uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);    // O[128,64] = P[128,KV] V[KV,64]
+    mbar_wait(q_full, 0);
+    const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 16);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&kv_full[st], ph);
+      tc_fence_after();
+      const uint32_t sk = smem_u32(sKV + st * 2 * Cfg::KV_BYTES);
+      const uint64_t dk = make_smem_desc_sw128(sk, 1024, 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base + Cfg::COL_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      tc_commit(s_full);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      // V tile [KV rows][64 d] is an MN-major B operand: 16 kv rows (one MMA K step) = 2048 B
+      const uint64_t dv = make_smem_desc_sw128(sk + Cfg::KV_BYTES, 1024, 1024);
+#pragma unroll
+      for (int k = 0; k < KV / 16; ++k)
+        mma_f16_ts(tmem_base + Cfg::COL_O, tmem_base + Cfg::COL_P + 8 * k, dv + 128 * k, idesc_o, k != 0);
+      tc_commit(&kv_empty[st]);
+      tc_commit(o_full);
+    }
+  } else if (warp >= 2) {
+    // ------------------------------ softmax / output ------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // (64^-1/4)^2 * log2(e)
+    float m_run = -INFINITY, l_run = 0.f;
+    float O[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) O[i] = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(KV, p.T - j * KV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KV; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * kScaleLog2);
+      const float alpha = exp2f(m_run - m_new);
+      // pass 2: probabilities -> fp16 -> TMEM (A operand of P V)
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KV; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, r);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(r[i]) * kScaleLog2 - m_new);
+          float p1 = exp2f(__uint_as_float(r[i + 1]) * kScaleLog2 - m_new);
+          if (c + i >= kv_valid) p0 = 0.f;
+          if (c + i + 1 >= kv_valid) p1 = 0.f;
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_h2(p0, p1);
+        }
+        tmem_st_32x32b_x16(lane_addr + Cfg::COL_P + (c >> 1), pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_O + c, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[c + i] = O[c + i] * alpha + __uint_as_float(r[i]);
+      }
+    }
+    const int t = qt * 128 + row;
+    if (t < p.T) {
+      const float inv = 1.0f / l_run;
+      __half* o = p.out + (static_cast<size_t>(n) * p.T + t) * p.C + head * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 v;
+        v.x = pack_h2(O[i] * inv, O[i + 1] * inv);
+        v.y = pack_h2(O[i + 2] * inv, O[i + 3] * inv);
+        v.z = pack_h2(O[i + 4] * inv, O[i + 5] * inv);
+        v.w = pack_h2(O[i + 6] * inv, O[i + 7] * inv);
+        *reinterpret_cast<uint4*>(o + i) = v;
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace ivid

@@ -1,0 +1,248 @@
+// HBM-bound element-wise kernels of the ADM UNet hot path (NHWC fp32 residual stream -> fp16 MMA operands).
+//
+//   gn_stats_kernel  : per-(sample, channel) sum / sum-of-squares of an fp32 NHWC tensor (double accumulators).
+//                      GroupNorm32 statistics (reference adm.py:36-41) are later formed per group from these, which
+//                      is what makes GroupNorm over a *virtual* channel concat (groups straddling the seam,
+//                      adm.py:563 + :158) free of any concat copy.
+//   gn_coeff_kernel  : per-(sample, channel) affine y = x*A + B that folds mean/rstd, gamma/beta and the FiLM
+//                      scale/shift  h = GN(h)*(1+scale)+shift  (adm.py:216-217).
+//   gn_apply_kernel  : y = [SiLU](x*A+B) written as fp16 NHWC (the conv A operand), optionally through the ResBlock's
+//                      nearest-2x upsample / 2x2 average pool (adm.py:203-208), optionally also emitting the raw input
+//                      as fp16 (operand of the 1x1 skip conv) and/or as resampled fp32 (identity skip of up/down blocks).
+//   pack_input_kernel: NCHW fp32 network input -> NHWC fp16 padded to 64 channels (adm.py:557, x.type(dtype)).
+#pragma once
+#include "common.cuh"
+
+namespace ivid {
+
+// ----------------------------------------------------------------------------------------------
+// per-channel statistics.  grid = (ceil(HW / PIX_PER_BLOCK), N), block = 256.
+// ----------------------------------------------------------------------------------------------
+constexpr int kStatsPixPerBlock = 256;
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
+                                                       int HW, int C) {
+  // thread layout: tx over C/4 float4 columns, ty over pixel rows
+  __shared__ float sred[256 * 8];   // [rows][cols][8] partials -> reduced over rows
+  const int n = blockIdx.y;
+  const int c4 = C >> 2;
+  const int cols = c4 < 256 ? c4 : 256;        // threads across channels
+  const int rows = 256 / cols;                 // pixel rows handled concurrently
+  const int tx = threadIdx.x % cols;
+  const int ty = threadIdx.x / cols;
+  const int p0 = blockIdx.x * kStatsPixPerBlock;
+  const int p1 = min(p0 + kStatsPixPerBlock, HW);
+  const float* base = x + (static_cast<size_t>(n) * HW) * C;
+  for (int cc = tx; cc < c4; cc += cols) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ty < rows) {
+      for (int p = p0 + ty; p < p1; p += rows) {
+        const float4 v = ldg_f4(base + static_cast<size_t>(p) * C + cc * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+      }
+    }
+    // reduce over ty through shared memory (rows <= 8 for C >= 128)
+    float* sm = sred;   // [rows][cols][8]
+    if (ty < rows) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sm[(ty * cols + tx) * 8 + j] = s[j];
+        sm[(ty * cols + tx) * 8 + 4 + j] = q[j];
+      }
+    }
+    __syncthreads();
+    if (ty == 0) {
+      double ds[4], dq[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ds[j] = 0.0; dq[j] = 0.0; }
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ds[j] += static_cast<double>(sm[(r * cols + tx) * 8 + j]);
+          dq[j] += static_cast<double>(sm[(r * cols + tx) * 8 + 4 + j]);
+        }
+      }
+      double* o = stats + (static_cast<size_t>(n) * C + cc * 4) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(o + 2 * j, ds[j]);
+        atomicAdd(o + 2 * j + 1, dq[j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// GroupNorm coefficients.  grid = N, block = 256.  Channels c in [0, C0) come from stats0, [C0, C0+C1) from stats1.
+//   A[n][c] = rstd*gamma*(1+scale),  B[n][c] = (beta - mean*rstd*gamma)*(1+scale) + shift
+// film: [N][film_ld] table; scale = film[n][film_off + c], shift = film[n][film_off + C + c]  (torch.chunk(emb_out, 2)).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_coeff_kernel(const double* __restrict__ stats0, const double* __restrict__ stats1,
+                                                       int C0, int C1, int groups, double inv_count, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ film, int film_ld, int film_off,
+                                                       float2* __restrict__ ab) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.x;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double* st = (c < C0) ? stats0 + (static_cast<size_t>(n) * C0 + c) * 2
+                                  : stats1 + (static_cast<size_t>(n) * C1 + (c - C0)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const double cnt_inv = inv_count / cpg;
+    const double mean = s * cnt_inv;
+    double var = q * cnt_inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a0 = s_rstd[g] * gamma[c];
+    const float b0 = beta[c] - s_mean[g] * a0;
+    float a = a0, b = b0;
+    if (film != nullptr) {
+      const float sc = 1.0f + film[static_cast<size_t>(n) * film_ld + film_off + c];
+      const float sh = film[static_cast<size_t>(n) * film_ld + film_off + C + c];
+      a = a0 * sc;
+      b = b0 * sc + sh;
+    }
+    ab[static_cast<size_t>(n) * C + c] = make_float2(a, b);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU, +resample).  One thread = 8 channels of one OUTPUT pixel.
+//   mode 0: same resolution; 1: nearest 2x upsample (Ho = 2H); 2: 2x2 average pool (Ho = H/2)
+// ----------------------------------------------------------------------------------------------
+struct GnApplyParams {
+  const float* x0; const float* x1;     // fp32 NHWC sources (virtual concat along C); x1 may be null (C1 = 0)
+  int C0, C1;
+  int N, H, W;                          // INPUT spatial size
+  int mode;                             // 0 same, 1 up, 2 down
+  int silu;
+  const float2* ab;                     // [N][C] coefficients
+  __half* out_act;                      // fp16 [N][Ho][Wo][C]
+  __half* out_raw16;                    // optional fp16 raw copy (same-resolution only) [N][H][W][C]
+  float* out_raw32;                     // optional fp32 raw (resampled) [N][Ho][Wo][C]
+};
+
+__device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int w, int c, float (&v)[8]) {
+  const float* src;
+  int cc, ld;
+  if (c < p.C0) { src = p.x0; cc = c; ld = p.C0; } else { src = p.x1; cc = c - p.C0; ld = p.C1; }
+  const float* q = src + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * ld + cc;
+  const float4 a = ldg_f4(q), b = ldg_f4(q + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  const int C = p.C0 + p.C1;
+  const int c8 = C >> 3;
+  const int Ho = p.mode == 1 ? p.H * 2 : (p.mode == 2 ? p.H / 2 : p.H);
+  const int Wo = p.mode == 1 ? p.W * 2 : (p.mode == 2 ? p.W / 2 : p.W);
+  const size_t total = static_cast<size_t>(p.N) * Ho * Wo * c8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % c8);
+    size_t pix = idx / c8;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    const int c = cg * 8;
+    float A[8], B[8];
+    {
+      const float4* abp = reinterpret_cast<const float4*>(p.ab + static_cast<size_t>(n) * C + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(abp + j);
+        A[2 * j] = t.x; B[2 * j] = t.y; A[2 * j + 1] = t.z; B[2 * j + 1] = t.w;
+      }
+    }
+    float act[8], raw[8];
+    if (p.mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { act[j] = 0.f; raw[j] = 0.f; }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float v[8];
+          load8(p, n, ho * 2 + dy, wo * 2 + dx, c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = fmaf(v[j], A[j], B[j]);
+            if (p.silu) y = silu_f(y);
+            act[j] += y;
+            raw[j] += v[j];
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { act[j] *= 0.25f; raw[j] *= 0.25f; }
+    } else {
+      const int hi = p.mode == 1 ? (ho >> 1) : ho;
+      const int wi = p.mode == 1 ? (wo >> 1) : wo;
+      load8(p, n, hi, wi, c, raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(raw[j], A[j], B[j]);
+        if (p.silu) y = silu_f(y);
+        act[j] = y;
+      }
+    }
+    const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c;
+    uint4 pk;
+    pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
+    pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
+    *reinterpret_cast<uint4*>(p.out_act + o) = pk;
+    if (p.out_raw16 != nullptr) {
+      uint4 pr;
+      pr.x = pack_h2(raw[0], raw[1]); pr.y = pack_h2(raw[2], raw[3]);
+      pr.z = pack_h2(raw[4], raw[5]); pr.w = pack_h2(raw[6], raw[7]);
+      *reinterpret_cast<uint4*>(p.out_raw16 + o) = pr;
+    }
+    if (p.out_raw32 != nullptr) {
+      stg_f4(p.out_raw32 + o, make_float4(raw[0], raw[1], raw[2], raw[3]));
+      stg_f4(p.out_raw32 + o + 4, make_float4(raw[4], raw[5], raw[6], raw[7]));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// network input: fp32 NCHW [Nx][Cin][H][W] -> fp16 NHWC [N][H][W][64] (zero padded channels); sample n reads n % Nx
+// (lets the two classifier-free-guidance halves share one x without a concat copy).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int N,
+                                                         int Nx, int Cin, int HW) {
+  const size_t total = static_cast<size_t>(N) * HW;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / HW);
+    const int p = static_cast<int>(idx % HW);
+    const float* src = x + (static_cast<size_t>(n % Nx) * Cin) * HW + p;
+    __half* dst = out + idx * 64;
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w[j] = 0u;
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {   // Cin <= 16 (4 / 8 / 10 on this path)
+      const float a = (c < Cin) ? src[static_cast<size_t>(c) * HW] : 0.f;
+      const float b = (c + 1 < Cin) ? src[static_cast<size_t>(c + 1) * HW] : 0.f;
+      w[c >> 1] = pack_h2(a, b);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  }
+}
+
+}  // namespace ivid

@@ -1,0 +1,203 @@
+// Kernel instantiation + host launch wrappers.
+#include "ops.h"
+
+#include <algorithm>
+#include <mutex>
+
+#include "attention.cuh"
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "embed.cuh"
+
+namespace ivid {
+
+// --------------------------------------------------------------------------------------------------
+// conv implicit GEMM
+// --------------------------------------------------------------------------------------------------
+struct ConvLaunch {
+  CUtensorMap mapA0, mapA1, mapB;
+  ConvGemmParams p;
+  int BN;
+  int grid;
+};
+
+int conv_pad_cout(int cout) {
+  if (cout >= 64) return ((cout + 63) / 64) * 64;
+  return ((cout + 15) / 16) * 16;
+}
+int conv_pick_bn(int cout_pad) {
+  if (cout_pad % 256 == 0) return 256;
+  if (cout_pad % 128 == 0) return 128;
+  if (cout_pad % 64 == 0) return 64;
+  if (cout_pad % 16 == 0 && cout_pad <= 48) return 16;
+  throw Error(kErrInvalidArgument, "conv: unsupported padded Cout " + std::to_string(cout_pad));
+}
+
+template <int BN>
+static void set_conv_attr() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvGemmCfg<BN>::SMEM_BYTES));
+  });
+}
+
+ConvLaunch* conv_launch_create(const ConvDesc& d) {
+  IVID_REQUIRE(d.C0 > 0 && d.C0 % 64 == 0, "conv: segment-0 channels must be a positive multiple of 64");
+  IVID_REQUIRE(d.C1 % 64 == 0, "conv: segment-1 channels must be a multiple of 64");
+  IVID_REQUIRE(d.taps0 == 9 || d.taps0 == 1, "conv: only 3x3 (pad 1) and 1x1 kernels are on this path");
+  IVID_REQUIRE(d.taps1 == 9 || d.taps1 == 1, "conv: only 3x3 (pad 1) and 1x1 kernels are on this path");
+  auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  IVID_REQUIRE(is_pow2(d.H) && is_pow2(d.W), "conv: spatial size must be a power of two");
+  auto* l = new ConvLaunch();
+  ConvGemmParams& p = l->p;
+  p.N = d.N; p.H = d.H; p.W = d.W;
+  p.TW = std::min(d.W, 16);
+  p.TH = std::min(d.H, 128 / p.TW);
+  p.TN = 128 / (p.TW * p.TH);
+  p.tiles_w = d.W / p.TW;
+  p.tiles_h = d.H / p.TH;
+  p.tiles_n = (d.N + p.TN - 1) / p.TN;
+  l->BN = conv_pick_bn(d.cout_pad);
+  p.n_blocks = d.cout_pad / l->BN;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  p.seg_chunks[0] = d.C0 / 64; p.seg_taps[0] = d.taps0;
+  p.seg_chunks[1] = d.C1 / 64; p.seg_taps[1] = d.C1 > 0 ? d.taps1 : 0;
+  p.Cout = d.cout; p.ldc = d.ldc; p.ldr = d.ldr; p.out_mode = d.out_mode;
+  p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+  IVID_REQUIRE(d.out_mode == 2 || (d.cout % 8 == 0 && d.ldc % 8 == 0), "conv: NHWC output needs Cout % 8 == 0");
+  const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0);
+  l->mapA0 = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
+  l->mapA1 = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : l->mapA0;
+  l->mapB = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN);
+  l->grid = std::min(p.num_tiles, sm_count());
+  return l;
+}
+void conv_launch_destroy(ConvLaunch* l) { delete l; }
+
+template <int BN>
+static void run_conv(const ConvLaunch* l, cudaStream_t s) {
+  set_conv_attr<BN>();
+  conv_gemm_kernel<BN><<<l->grid, ConvGemmCfg<BN>::THREADS, ConvGemmCfg<BN>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1,
+                                                                                                l->mapB, l->p);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {
+  ConvLaunch tmp = *l;
+  tmp.p.out = out;
+  conv_launch_run(&tmp, s);
+}
+void conv_launch_run(const ConvLaunch* l, cudaStream_t s) {
+  switch (l->BN) {
+    case 256: run_conv<256>(l, s); break;
+    case 128: run_conv<128>(l, s); break;
+    case 64: run_conv<64>(l, s); break;
+    default: run_conv<16>(l, s); break;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// attention
+// --------------------------------------------------------------------------------------------------
+struct AttnLaunch {
+  CUtensorMap mapQ, mapKV;
+  AttnParams p;
+  int KV;
+  int grid;
+};
+
+AttnLaunch* attn_launch_create(const void* qkv, int N, int T, int C, void* out) {
+  IVID_REQUIRE(C % 64 == 0, "attention: channels must be a multiple of the head width 64");
+  IVID_REQUIRE(T >= 64 && T % 64 == 0, "attention: sequence length must be a multiple of 64");
+  auto* l = new AttnLaunch();
+  l->KV = (T % 128 == 0) ? 128 : 64;
+  l->p.N = N; l->p.T = T; l->p.C = C; l->p.heads = C / 64;
+  l->p.q_tiles = (T + 127) / 128;
+  l->p.out = reinterpret_cast<__half*>(out);
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(T), static_cast<uint64_t>(N)};
+  const uint64_t str[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(T) * 3 * C * 2};
+  const uint32_t boxq[3] = {64, 128, 1};
+  const uint32_t boxkv[3] = {64, static_cast<uint32_t>(l->KV), 1};
+  l->mapQ = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(qkv), dims, str, boxq,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+  l->mapKV = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(qkv), dims, str, boxkv,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+  l->grid = N * l->p.heads * l->p.q_tiles;
+  return l;
+}
+void attn_launch_destroy(AttnLaunch* l) { delete l; }
+
+template <int KV>
+static void run_attn(const AttnLaunch* l, cudaStream_t s) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnCfg<KV>::SMEM_BYTES));
+  });
+  attention_kernel<KV><<<l->grid, AttnCfg<KV>::THREADS, AttnCfg<KV>::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+void attn_launch_run(const AttnLaunch* l, cudaStream_t s) {
+  if (l->KV == 128) run_attn<128>(l, s);
+  else run_attn<64>(l, s);
+}
+
+// --------------------------------------------------------------------------------------------------
+// element-wise / embedding
+// --------------------------------------------------------------------------------------------------
+static int ew_grid(size_t work_items, int block) {
+  const size_t blocks = (work_items + block - 1) / block;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  return static_cast<int>(std::max<size_t>(1, std::min(blocks, cap)));
+}
+
+void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaStream_t s) {
+  IVID_REQUIRE(C % 4 == 0, "gn_stats: C % 4");
+  dim3 grid((HW + kStatsPixPerBlock - 1) / kStatsPixPerBlock, N);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(x, stats, HW, C);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_gn_coeff(const double* stats0, const double* stats1, int C0, int C1, int N, int groups, int HW, float eps,
+                     const float* gamma, const float* beta, const float* film, int film_ld, int film_off, void* ab,
+                     cudaStream_t s) {
+  IVID_REQUIRE(groups <= 64 && (C0 + C1) % groups == 0, "group norm: groups must divide channels (<= 64 groups)");
+  gn_coeff_kernel<<<N, 256, 0, s>>>(stats0, stats1, C0, C1, groups, 1.0 / static_cast<double>(HW), eps, gamma, beta,
+                                    film, film_ld, film_off, reinterpret_cast<float2*>(ab));
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
+  IVID_REQUIRE(d.C0 % 8 == 0 && d.C1 % 8 == 0, "gn_apply: channel counts must be multiples of 8");
+  GnApplyParams p;
+  p.x0 = d.x0; p.x1 = d.x1; p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
+  p.silu = d.silu; p.ab = reinterpret_cast<const float2*>(d.ab);
+  p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);
+  p.out_raw32 = d.out_raw32;
+  const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
+  const int Wo = d.mode == 1 ? d.W * 2 : (d.mode == 2 ? d.W / 2 : d.W);
+  const size_t items = static_cast<size_t>(d.N) * Ho * Wo * ((d.C0 + d.C1) / 8);
+  gn_apply_kernel<<<ew_grid(items, 256), 256, 0, s>>>(p);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s) {
+  IVID_REQUIRE(Cin <= 16, "pack_input: at most 16 input channels");
+  pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,
+                                                                             Cin, HW);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float* out, int N, cudaStream_t s) {
+  posenc_kernel<<<N, 128, 0, s>>>(t, Nt, freqs, half, out, N);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_linear(const float* in, const float* W, const float* bias, float* out, int N, int K, int O, int silu_in,
+                   const float* label_emb, const int64_t* classes, int Ncls, cudaStream_t s) {
+  dim3 grid((O + 7) / 8, (N + 31) / 32);
+  linear_rows_kernel<<<grid, 256, 0, s>>>(in, W, bias, out, N, K, O, silu_in, label_emb, classes, Ncls);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace ivid

@@ -1,0 +1,64 @@
+// Host-side launch descriptors for the sm_100a kernels (built once at plan time, replayed every step).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "host_util.h"
+
+namespace ivid {
+
+// mirrors of the device parameter structs (defined in the .cuh files; redeclared opaque here through includes in ops.cu)
+struct ConvLaunch;
+struct AttnLaunch;
+
+struct ConvDesc {
+  const void* act0 = nullptr; int C0 = 0; int taps0 = 9;   // segment 0: fp16 NHWC activation, 9 = 3x3, 1 = 1x1
+  const void* act1 = nullptr; int C1 = 0; int taps1 = 1;   // optional segment 1 (1x1 skip over another tensor)
+  const void* weight = nullptr;                            // fp16 [cout_pad][Ktot], Ktot = taps0*C0 + taps1*C1
+  int cout_pad = 0;
+  int cout = 0;                                            // valid output channels
+  const float* bias = nullptr;                             // [cout_pad]
+  const float* residual = nullptr; int ldr = 0;            // fp32 NHWC
+  void* out = nullptr; int ldc = 0; int out_mode = 0;      // 0 fp32 NHWC, 1 fp16 NHWC, 2 fp32 NCHW
+  int N = 0, H = 0, W = 0;
+};
+
+// opaque, heap-allocated launch records (hold the CUtensorMaps)
+ConvLaunch* conv_launch_create(const ConvDesc& d);
+void conv_launch_destroy(ConvLaunch* l);
+void conv_launch_run(const ConvLaunch* l, cudaStream_t s);
+void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s);   // same launch, output pointer overridden
+int conv_pick_bn(int cout_pad);
+int conv_pad_cout(int cout);
+
+AttnLaunch* attn_launch_create(const void* qkv, int N, int T, int C, void* out);
+void attn_launch_destroy(AttnLaunch* l);
+void attn_launch_run(const AttnLaunch* l, cudaStream_t s);
+
+void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaStream_t s);
+void launch_gn_coeff(const double* stats0, const double* stats1, int C0, int C1, int N, int groups, int HW, float eps,
+                     const float* gamma, const float* beta, const float* film, int film_ld, int film_off, void* ab,
+                     cudaStream_t s);
+struct GnApplyDesc {
+  const float* x0 = nullptr; const float* x1 = nullptr; int C0 = 0, C1 = 0;
+  int N = 0, H = 0, W = 0; int mode = 0; int silu = 1;
+  const void* ab = nullptr;
+  void* out_act = nullptr; void* out_raw16 = nullptr; float* out_raw32 = nullptr;
+};
+void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s);
+void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s);
+
+struct CondPackDesc {
+  const float* x = nullptr; const float* y = nullptr; const float* mask = nullptr; const float* mask_rgb = nullptr;
+  const float* noise = nullptr; void* out = nullptr; int N = 0, Nx = 0, H = 0, W = 0; int kind = 0;
+  uint64_t seed = 0; uint32_t stream = 0; const int* stream_dev = nullptr;
+};
+void launch_cond_pack(const CondPackDesc& d, cudaStream_t s);   // sampler.cu
+
+void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float* out, int N, cudaStream_t s);
+void launch_linear(const float* in, const float* W, const float* bias, float* out, int N, int K, int O, int silu_in,
+                   const float* label_emb, const int64_t* classes, int Ncls, cudaStream_t s);
+
+}  // namespace ivid

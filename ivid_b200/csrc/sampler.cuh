@@ -1,0 +1,256 @@
+// Fused denoising-step kernels: classifier-free-guidance mix + DDPM / DDIM update (+ multiview replace/constrain
+// guidance) in ONE HBM pass over [N,4,H,W], coefficients read from a device-resident table (no per-step H2D).
+//   reference: ClassifierFreeGuidance.model_inference classifier_free_guidance.py:39-42
+//              DdpmSampler.p_mean_variance / sample_once   samplers/ddpm.py:85-100,127-131
+//              DdimSampler.sample_once                      samplers/ddim.py:81-103
+//              InpaintCFG.make_cond_inputs                  frameworks/inpaint_cfg.py:33-49
+//              SuperResCFG.make_cond_inputs                 frameworks/sr_cfg.py:31-36
+#pragma once
+#include "common.cuh"
+
+namespace ivid {
+
+// ----------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG + Box-Muller (in-kernel N(0,1) for the production path; parity tests inject noise).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x) + 0.5f) * 2.3283064365386963e-10f; }
+// four N(0,1) draws for (seed, stream, idx)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t stream, uint32_t idx) {
+  const uint4 r = philox4x32_10(make_uint4(idx, stream, 0u, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const float r0 = sqrtf(-2.0f * logf(u01(r.x))), a0 = 6.283185307179586f * u01(r.y);
+  const float r1 = sqrtf(-2.0f * logf(u01(r.z))), a1 = 6.283185307179586f * u01(r.w);
+  float s0, c0, s1, c1;
+  sincosf(a0, &s0, &c0);
+  sincosf(a1, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// Per-timestep coefficient row (fp32 casts of the reference's float64 numpy tables).
+struct StepCoef {
+  float sqrt_recip_acp;      // sqrt(1/acp[t])
+  float sqrt_recipm1_acp;    // sqrt(1/acp[t] - 1)
+  float post_mean_coef1;     // DDPM
+  float post_mean_coef2;     // DDPM
+  float post_logvar;         // DDPM posterior_log_variance_clipped[t]
+  float acp;                 // alphas_cumprod[t]
+  float acp_prev;            // alphas_cumprod_prev[t]  (acp_prev[0] = 1)
+  float pad;
+};
+
+struct GuideParams {           // DDIM multiview guidance (all maps fp32 NCHW, nullptr = disabled)
+  const float* rgb;            // [N,3,H,W]
+  const float* rgb_mask;       // [N,1,H,W]
+  const float* depth;          // [N,1,H,W]
+  const float* depth_mask;     // [N,1,H,W]
+  const float* convex;         // [N,1,H,W]
+  float w_rgb, w_rgb_c;        // w and (1-w) as the reference's python floats cast to fp32
+  float w_depth, w_depth_c;
+  float w_convex, w_convex_c;
+};
+
+struct StepParams {
+  const float* x_t;            // [N,C,H,W]
+  const float* eps;            // [2N or N,C,H,W]: rows [0,N) conditional, [N,2N) unconditional when cfg
+  const float* noise;          // [N,C,H,W] injected N(0,1) or nullptr -> Philox
+  float* x_prev;               // [N,C,H,W]
+  float* pred_x0;              // optional
+  const StepCoef* table;       // [T]
+  const int* t_index;          // device scalar: table row for the model timestep (t for DDPM, t-1 for DDIM)
+  const int* t_prev;           // DDIM: device scalar t_prev (acp_prev row); DDPM: unused
+  int N, C, HW;
+  int cfg;                     // 1: eps = (1+s)*eps_c - s*eps_u
+  float strength;
+  int clip;
+  float eta;
+  uint64_t seed;
+  uint32_t stream;             // Philox stream id (step counter supplied by caller) when noise == nullptr
+  const int* stream_dev;       // optional device step counter added to `stream`
+  GuideParams g;
+};
+
+__device__ __forceinline__ float mix_eps(const StepParams& p, size_t i, size_t total) {
+  const float ec = p.eps[i];
+  if (!p.cfg) return ec;
+  // (1 + strength) * eps_c - strength * eps_u     (only evaluated with strength > 0)
+  return (1.0f + p.strength) * ec - p.strength * p.eps[total + i];
+}
+
+// one thread = 4 consecutive pixels of one (n, c) plane
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const StepParams p) {
+  const size_t total = static_cast<size_t>(p.N) * p.C * p.HW;
+  const StepCoef k = p.table[*p.t_index];
+  const float nz = (*p.t_index != 0) ? 1.0f : 0.0f;
+  const float sd = expf(0.5f * k.post_logvar);
+  const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
+  for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 * 4 < total;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = i4 * 4;
+    float z[4];
+    if (p.noise != nullptr) {
+      const float4 t = ldg_f4(p.noise + i);
+      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+    } else {
+      const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(i4));
+      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+    }
+    float xo[4], x0o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xt = p.x_t[i + j];
+      const float e = mix_eps(p, i + j, total);
+      float x0 = k.sqrt_recip_acp * xt - k.sqrt_recipm1_acp * e;
+      if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+      const float mean = k.post_mean_coef1 * x0 + k.post_mean_coef2 * xt;
+      xo[j] = mean + nz * sd * z[j];
+      x0o[j] = x0;
+    }
+    stg_f4(p.x_prev + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+    if (p.pred_x0) stg_f4(p.pred_x0 + i, make_float4(x0o[0], x0o[1], x0o[2], x0o[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256) ddim_step_kernel(const StepParams p) {
+  const size_t total = static_cast<size_t>(p.N) * p.C * p.HW;
+  const StepCoef k = p.table[*p.t_index];
+  const int tprev = *p.t_prev;
+  const float nz = (tprev != 0) ? 1.0f : 0.0f;
+  const float ab = k.acp;
+  const float abp = (tprev == 0) ? 1.0f : p.table[tprev - 1].acp;   // alphas_cumprod_prev[t_prev]
+  const float sigma = p.eta * sqrtf((1.0f - abp) / (1.0f - ab)) * sqrtf(1.0f - ab / abp);
+  const float c_x0 = sqrtf(abp);
+  const float c_eps = sqrtf(1.0f - abp - sigma * sigma);
+  const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
+  for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 * 4 < total;
+       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = i4 * 4;
+    const int plane = static_cast<int>(i / p.HW);      // n*C + c
+    const int n = plane / p.C, c = plane % p.C;
+    const size_t pix = i - static_cast<size_t>(plane) * p.HW;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sigma != 0.0f) {
+      if (p.noise != nullptr) {
+        const float4 t = ldg_f4(p.noise + i);
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+      } else {
+        const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(i4));
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+      }
+    }
+    float xo[4], x0o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xt = p.x_t[i + j];
+      const float e = mix_eps(p, i + j, total);
+      float x0 = k.sqrt_recip_acp * xt - k.sqrt_recipm1_acp * e;
+      if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+      if (c < 3) {
+        if (p.g.rgb != nullptr) {
+          const float y = p.g.rgb[(static_cast<size_t>(n) * 3 + c) * p.HW + pix + j];
+          const float m = p.g.rgb_mask[static_cast<size_t>(n) * p.HW + pix + j];
+          x0 = (1.0f - nz) * x0 + nz * ((p.g.w_rgb * y + p.g.w_rgb_c * x0) * m + x0 * (1.0f - m));
+        }
+      } else if (p.g.depth != nullptr) {
+        const float y = p.g.depth[static_cast<size_t>(n) * p.HW + pix + j];
+        const float m = p.g.depth_mask[static_cast<size_t>(n) * p.HW + pix + j];
+        x0 = (p.g.w_depth * y + p.g.w_depth_c * x0) * m + x0 * (1.0f - m);
+        if (p.g.convex != nullptr) {
+          const float cv = p.g.convex[static_cast<size_t>(n) * p.HW + pix + j];
+          x0 = x0 * m + (p.g.w_convex * fmaxf(x0, cv) + p.g.w_convex_c * x0) * (1.0f - m);
+        }
+      }
+      const float e2 = (k.sqrt_recip_acp * xt - x0) / k.sqrt_recipm1_acp;
+      const float mean = c_x0 * x0 + c_eps * e2;
+      xo[j] = mean + nz * sigma * z[j];
+      x0o[j] = x0;
+    }
+    stg_f4(p.x_prev + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+    if (p.pred_x0) stg_f4(p.pred_x0 + i, make_float4(x0o[0], x0o[1], x0o[2], x0o[3]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Conditional-model input assembly, fused with the NCHW fp32 -> NHWC fp16(64 ch) packing.
+// ----------------------------------------------------------------------------------------------
+struct CondPackParams {
+  const float* x;         // [Nx,4,H,W]
+  const float* y;         // inpaint: [Nx,4,H,W] warped RGBD;  superres: [Nx,4,H/2,W/2] low-res RGBD
+  const float* mask;      // inpaint [Nx,1,H,W]
+  const float* mask_rgb;  // inpaint [Nx,1,H,W] or nullptr (then mask is used and no mask_rgb channel is emitted)
+  const float* noise;     // inpaint: injected [Nx,4,H,W] (rgb noise 3 + depth noise 1) or nullptr -> Philox
+  __half* out;            // [N,H,W,64]
+  int N, Nx, H, W;
+  int kind;               // 1 = InpaintCFG, 2 = SuperResCFG
+  uint64_t seed;
+  uint32_t stream;
+  const int* stream_dev;
+};
+
+__global__ void __launch_bounds__(256) cond_pack_kernel(const CondPackParams p) {
+  const int HW = p.H * p.W;
+  const size_t total = static_cast<size_t>(p.N) * HW;
+  const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / HW) % p.Nx;
+    const int pix = static_cast<int>(idx % HW);
+    float ch[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ch[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ch[c] = p.x[(static_cast<size_t>(n) * 4 + c) * HW + pix];
+    if (p.kind == 1) {
+      const float m = p.mask[static_cast<size_t>(n) * HW + pix];
+      const float mr = p.mask_rgb ? p.mask_rgb[static_cast<size_t>(n) * HW + pix] : m;
+      float z[4];
+      if (p.noise != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) z[c] = p.noise[(static_cast<size_t>(n) * 4 + c) * HW + pix];
+      } else {
+        const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(static_cast<size_t>(n) * HW + pix));
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+      }
+      int o = 4;
+      if (p.mask_rgb) ch[o++] = mr;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        ch[o++] = p.y[(static_cast<size_t>(n) * 4 + c) * HW + pix] * mr + z[c] * (1.0f - mr);
+      ch[o++] = p.y[(static_cast<size_t>(n) * 4 + 3) * HW + pix] * m + z[3] * (1.0f - m);
+      ch[o++] = m;
+    } else {
+      // bilinear 2x upsample, align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0 (ATen upsample_bilinear2d)
+      const int h = pix / p.W, w = pix % p.W;
+      const int Hs = p.H / 2, Ws = p.W / 2;
+      float sy = (h + 0.5f) * 0.5f - 0.5f; if (sy < 0.f) sy = 0.f;
+      float sx = (w + 0.5f) * 0.5f - 0.5f; if (sx < 0.f) sx = 0.f;
+      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+      const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+      const float ly = sy - y0, lx = sx - x0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* s = p.y + (static_cast<size_t>(n) * 4 + c) * Hs * Ws;
+        const float v = (1.f - ly) * ((1.f - lx) * s[y0 * Ws + x0] + lx * s[y0 * Ws + x1]) +
+                        ly * ((1.f - lx) * s[y1 * Ws + x0] + lx * s[y1 * Ws + x1]);
+        ch[4 + c] = v;
+      }
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(p.out + idx * 64);
+    d4[0] = make_uint4(pack_h2(ch[0], ch[1]), pack_h2(ch[2], ch[3]), pack_h2(ch[4], ch[5]), pack_h2(ch[6], ch[7]));
+    d4[1] = make_uint4(pack_h2(ch[8], ch[9]), pack_h2(ch[10], ch[11]), pack_h2(ch[12], ch[13]), pack_h2(ch[14], ch[15]));
+#pragma unroll
+    for (int j = 2; j < 8; ++j) d4[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+}  // namespace ivid

@@ -1,0 +1,692 @@
+#include "unet.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "json_min.h"
+
+namespace ivid {
+
+// ==================================================================================================
+// config
+// ==================================================================================================
+static UnetConfig parse_config(const std::string& text) {
+  JsonValue j;
+  try {
+    j = JsonParser(text).parse();
+  } catch (const std::exception& e) {
+    throw Error(kErrInvalidArgument, e.what());
+  }
+  IVID_REQUIRE(j.kind == JsonValue::kObject, "backbone config must be a JSON object");
+  // accept a whole reference config file ({"backbone": {"name", "args"}, ...}), its "backbone" object, or bare args
+  if (j.has("backbone") && j.at("backbone").kind == JsonValue::kObject) j = JsonValue(j.at("backbone"));
+  if (j.has("args") && j.at("args").kind == JsonValue::kObject) j = JsonValue(j.at("args"));
+  UnetConfig c;
+  auto geti = [&](const char* k, int& dst, bool required) {
+    if (j.has(k)) dst = static_cast<int>(j.at(k).num);
+    else IVID_REQUIRE(!required, std::string("backbone config: missing '") + k + "'");
+  };
+  auto getb = [&](const char* k, bool& dst) { if (j.has(k)) dst = j.at(k).kind == JsonValue::kBool ? j.at(k).b : j.at(k).num != 0; };
+  geti("image_size", c.image_size, true);
+  geti("in_channels", c.in_channels, true);
+  geti("model_channels", c.model_channels, true);
+  geti("out_channels", c.out_channels, true);
+  geti("num_res_blocks", c.num_res_blocks, true);
+  IVID_REQUIRE(j.has("attention_resolutions"), "backbone config: missing 'attention_resolutions'");
+  for (auto& v : j.at("attention_resolutions").arr) c.attention_resolutions.push_back(static_cast<int>(v.num));
+  if (j.has("channel_mult")) {
+    c.channel_mult.clear();
+    for (auto& v : j.at("channel_mult").arr) c.channel_mult.push_back(v.num);
+  }
+  if (j.has("dropout")) c.dropout = j.at("dropout").num;
+  getb("conv_resample", c.conv_resample);
+  geti("num_classes", c.num_classes, false);
+  getb("has_null_class", c.has_null_class);
+  if (c.num_classes == 0) c.has_null_class = false;       // adm.py:350
+  getb("use_fp16", c.use_fp16);
+  geti("num_groups", c.num_groups, false);
+  geti("num_heads", c.num_heads, false);                  // null -> keeps default (adm.py:330); unused with head channels
+  geti("num_head_channels", c.num_head_channels, false);
+  getb("use_scale_shift_norm", c.use_scale_shift_norm);
+  getb("resblock_updown", c.resblock_updown);
+  return c;
+}
+
+Unet::Unet(const std::string& cfg_json) : cfg_(parse_config(cfg_json)) { build_topology(); }
+
+int Unet::add_param(const std::string& name, std::vector<int64_t> shape, bool is_buffer) {
+  ParamSpec p;
+  p.name = name;
+  p.shape = std::move(shape);
+  p.is_buffer = is_buffer;
+  pindex_[name] = static_cast<int>(params_.size());
+  params_.push_back(std::move(p));
+  return static_cast<int>(params_.size()) - 1;
+}
+
+const ParamSpec& Unet::P(const std::string& name) const {
+  auto it = pindex_.find(name);
+  if (it == pindex_.end()) throw Error(kErrState, "internal: unknown parameter " + name);
+  const ParamSpec& p = params_[it->second];
+  if (!p.set) throw Error(kErrState, "parameter '" + name + "' was never set (load_state_dict incomplete)");
+  return p;
+}
+
+// State-dict schema + block structure.  Follows the constructor of the reference (adm.py:356-487) layer for layer so that
+// key names ("input_blocks.3.0.in_layers.0.weight", ...) and shapes match torch's registration order.
+void Unet::build_topology() {
+  const UnetConfig& c = cfg_;
+  if (!c.use_scale_shift_norm) throw Error(kErrNotImplemented, "use_scale_shift_norm=False is not on the sampling hot path");
+  if (!c.resblock_updown) throw Error(kErrNotImplemented, "resblock_updown=False is not on the sampling hot path");
+  IVID_REQUIRE(c.model_channels % 64 == 0, "model_channels must be a multiple of 64 (tensor-core K slab)");
+  IVID_REQUIRE(c.in_channels <= 16, "in_channels must be <= 16");
+  IVID_REQUIRE(c.num_groups >= 1 && c.num_groups <= 64, "num_groups must be in [1,64]");
+  const int mc = c.model_channels;
+  const int E = mc * 4;
+  embed_dim_ = E;
+
+  add_param("time_embed.0.freqs", {mc / 2}, /*is_buffer=*/true);
+  add_param("time_embed.1.weight", {E, mc});
+  add_param("time_embed.1.bias", {E});
+  add_param("time_embed.3.weight", {E, E});
+  add_param("time_embed.3.bias", {E});
+  if (c.num_classes > 0) add_param("label_emb.weight", {c.num_classes, E});
+
+  auto heads_ok = [&](int ch) {
+    const int hc = c.num_head_channels == -1 ? ch / std::max(1, c.num_heads) : c.num_head_channels;
+    if (hc != 64 || ch % 64 != 0)
+      throw Error(kErrNotImplemented, "attention head width must be 64 channels (num_head_channels=64)");
+  };
+  auto add_res = [&](const std::string& pfx, int cin, int cout, int mode) {
+    ResBlockDef r;
+    r.pfx = pfx; r.cin = cin; r.cout = cout; r.mode = mode;
+    IVID_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "channel counts must be multiples of 64");
+    IVID_REQUIRE(cin % c.num_groups == 0 && cout % c.num_groups == 0, "num_groups must divide channels");
+    add_param(pfx + ".in_layers.0.weight", {cin});
+    add_param(pfx + ".in_layers.0.bias", {cin});
+    add_param(pfx + ".in_layers.2.weight", {cout, cin, 3, 3});
+    add_param(pfx + ".in_layers.2.bias", {cout});
+    add_param(pfx + ".emb_layers.1.weight", {2 * cout, E});
+    add_param(pfx + ".emb_layers.1.bias", {2 * cout});
+    add_param(pfx + ".out_layers.0.weight", {cout});
+    add_param(pfx + ".out_layers.0.bias", {cout});
+    add_param(pfx + ".out_layers.3.weight", {cout, cout, 3, 3});
+    add_param(pfx + ".out_layers.3.bias", {cout});
+    r.skip_conv = (cin != cout);
+    if (r.skip_conv) {
+      add_param(pfx + ".skip_connection.weight", {cout, cin, 1, 1});
+      add_param(pfx + ".skip_connection.bias", {cout});
+    }
+    r.film_off = film_total_;
+    film_total_ += 2 * cout;
+    res_.push_back(r);
+    return static_cast<int>(res_.size()) - 1;
+  };
+  auto add_attn = [&](const std::string& pfx, int ch) {
+    heads_ok(ch);
+    AttnBlockDef a;
+    a.pfx = pfx; a.C = ch;
+    add_param(pfx + ".norm.weight", {ch});
+    add_param(pfx + ".norm.bias", {ch});
+    add_param(pfx + ".qkv.weight", {3 * ch, ch, 1});
+    add_param(pfx + ".qkv.bias", {3 * ch});
+    add_param(pfx + ".proj_out.weight", {ch, ch, 1});
+    add_param(pfx + ".proj_out.bias", {ch});
+    attn_.push_back(a);
+    return static_cast<int>(attn_.size()) - 1;
+  };
+  auto in_attn = [&](int ds) {
+    return std::find(c.attention_resolutions.begin(), c.attention_resolutions.end(), ds) != c.attention_resolutions.end();
+  };
+
+  int ch = static_cast<int>(c.channel_mult[0] * mc);
+  const int input_ch = ch;
+  in_ch_stem_ = ch;
+  add_param("input_blocks.0.0.weight", {ch, c.in_channels, 3, 3});
+  add_param("input_blocks.0.0.bias", {ch});
+  {
+    BlockDef b;
+    b.is_input = true;   // the stem conv: no layers, handled explicitly
+    blocks_.push_back(b);
+  }
+  int ds = c.image_size;
+  std::vector<int> input_block_chs{ch};
+  int ib = 1;
+  const int levels = static_cast<int>(c.channel_mult.size());
+  for (int level = 0; level < levels; ++level) {
+    const int outc = static_cast<int>(c.channel_mult[level] * mc);
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      BlockDef b;
+      b.is_input = true;
+      const std::string pfx = "input_blocks." + std::to_string(ib);
+      b.layers.push_back({1, add_res(pfx + ".0", ch, outc, 0)});
+      ch = outc;
+      if (in_attn(ds)) b.layers.push_back({2, add_attn(pfx + ".1", ch)});
+      blocks_.push_back(b);
+      input_block_chs.push_back(ch);
+      ++ib;
+    }
+    if (level != levels - 1) {
+      BlockDef b;
+      b.is_input = true;
+      b.layers.push_back({1, add_res("input_blocks." + std::to_string(ib) + ".0", ch, ch, 2)});
+      blocks_.push_back(b);
+      input_block_chs.push_back(ch);
+      ++ib;
+      ds /= 2;
+    }
+  }
+  {
+    BlockDef b;
+    b.layers.push_back({1, add_res("middle_block.0", ch, ch, 0)});
+    b.layers.push_back({2, add_attn("middle_block.1", ch)});
+    b.layers.push_back({1, add_res("middle_block.2", ch, ch, 0)});
+    blocks_.push_back(b);
+  }
+  int ob = 0;
+  for (int level = levels - 1; level >= 0; --level) {
+    const int outc = static_cast<int>(mc * c.channel_mult[level]);
+    for (int i = 0; i <= c.num_res_blocks; ++i) {
+      BlockDef b;
+      b.is_output = true;
+      const std::string pfx = "output_blocks." + std::to_string(ob);
+      const int ich = input_block_chs.back();
+      input_block_chs.pop_back();
+      int li = 0;
+      b.layers.push_back({1, add_res(pfx + "." + std::to_string(li++), ch + ich, outc, 0)});
+      ch = outc;
+      if (in_attn(ds)) b.layers.push_back({2, add_attn(pfx + "." + std::to_string(li++), ch)});
+      if (level != 0 && i == c.num_res_blocks) {
+        b.layers.push_back({1, add_res(pfx + "." + std::to_string(li++), ch, ch, 1)});
+        ds *= 2;
+      }
+      blocks_.push_back(b);
+      ++ob;
+    }
+  }
+  final_ch_ = ch;
+  IVID_REQUIRE(ch == input_ch, "final channel count must equal the stem width (adm.py:486 uses input_ch)");
+  add_param("out.0.weight", {ch});
+  add_param("out.0.bias", {ch});
+  add_param("out.2.weight", {c.out_channels, input_ch, 3, 3});
+  add_param("out.2.bias", {c.out_channels});
+}
+
+void Unet::set_param(const std::string& name, const float* data, const int64_t* shape, int ndim) {
+  auto it = pindex_.find(name);
+  if (it == pindex_.end()) throw Error(kErrInvalidArgument, "unexpected key in state_dict: " + name);
+  ParamSpec& p = params_[it->second];
+  bool same = static_cast<int>(p.shape.size()) == ndim;
+  for (int i = 0; same && i < ndim; ++i) same = p.shape[i] == shape[i];
+  if (!same) throw Error(kErrInvalidArgument, "size mismatch for " + name);
+  p.host.assign(data, data + p.numel());
+  p.set = true;
+}
+
+// ==================================================================================================
+// weight packing
+// ==================================================================================================
+namespace {
+struct ArenaBuilder {
+  std::vector<uint8_t> buf;
+  size_t alloc(size_t bytes) {
+    const size_t off = (buf.size() + 255) & ~size_t(255);
+    buf.resize(off + bytes, 0);
+    return off;
+  }
+  template <class T> T* at(size_t off) { return reinterpret_cast<T*>(buf.data() + off); }
+};
+
+// [Cout][Cin][k][k] fp32 -> rows of [taps][cin_pad] fp16 written at column `kcol0` of a [cout_pad][Ktot] matrix
+void pack_conv_rows(__half* dst, int Ktot, int kcol0, const float* w, int cout, int cin, int cin_pad, int ksz) {
+  const int taps = ksz * ksz;
+  for (int co = 0; co < cout; ++co)
+    for (int tap = 0; tap < taps; ++tap)
+      for (int ci = 0; ci < cin; ++ci)
+        dst[static_cast<size_t>(co) * Ktot + kcol0 + tap * cin_pad + ci] =
+            __float2half_rn(w[(static_cast<size_t>(co) * cin + ci) * taps + tap]);
+}
+}  // namespace
+
+void Unet::finalize(int device) {
+  IVID_CHECK_CUDA(cudaSetDevice(device));
+  for (const auto& p : params_)
+    if (!p.set) throw Error(kErrState, "parameter '" + p.name + "' was never set (load_state_dict incomplete)");
+  plans_.clear();
+  if (arena_) { cudaFree(arena_); arena_ = nullptr; }
+  device_ = device;
+  ArenaBuilder ab;
+  auto put_f32 = [&](const std::vector<float>& v, size_t pad_to = 0) {
+    const size_t n = std::max(v.size(), pad_to);
+    const size_t off = ab.alloc(n * 4);
+    std::memcpy(ab.at<float>(off), v.data(), v.size() * 4);
+    return off;
+  };
+  auto pack_gn = [&](const std::string& pfx, int C) {
+    GnW g; g.C = C;
+    g.g_off = put_f32(P(pfx + ".weight").host);
+    g.b_off = put_f32(P(pfx + ".bias").host);
+    return g;
+  };
+  // generic conv: main weight (ksz x ksz over cin, channel-padded to cin_pad) + optional 1x1 skip weight over cin2
+  auto pack_conv = [&](const std::string& wname, const std::string& bname, int cout, int cin, int cin_pad, int ksz,
+                       const std::string& skip_w, const std::string& skip_b, int cin2) {
+    ConvW cw;
+    cw.cout = cout;
+    cw.cout_pad = conv_pad_cout(cout);
+    cw.K = ksz * ksz * cin_pad + cin2;
+    cw.w_off = ab.alloc(static_cast<size_t>(cw.cout_pad) * cw.K * 2);
+    pack_conv_rows(ab.at<__half>(cw.w_off), cw.K, 0, P(wname).host.data(), cout, cin, cin_pad, ksz);
+    std::vector<float> bias(cw.cout_pad, 0.f);
+    const auto& b = P(bname).host;
+    for (int i = 0; i < cout; ++i) bias[i] = b[i];
+    if (cin2 > 0) {
+      pack_conv_rows(ab.at<__half>(cw.w_off), cw.K, ksz * ksz * cin_pad, P(skip_w).host.data(), cout, cin2, cin2, 1);
+      const auto& b2 = P(skip_b).host;
+      for (int i = 0; i < cout; ++i) bias[i] += b2[i];
+    }
+    cw.b_off = put_f32(bias);
+    return cw;
+  };
+  auto pack_lin = [&](const std::string& pfx) {
+    const ParamSpec& w = P(pfx + ".weight");
+    LinW l; l.O = static_cast<int>(w.shape[0]); l.K = static_cast<int>(w.shape[1]);
+    l.w_off = put_f32(w.host);
+    l.b_off = put_f32(P(pfx + ".bias").host);
+    return l;
+  };
+
+  freqs_off_ = put_f32(P("time_embed.0.freqs").host);
+  te1_ = pack_lin("time_embed.1");
+  te2_ = pack_lin("time_embed.3");
+  if (cfg_.num_classes > 0) label_off_ = put_f32(P("label_emb.weight").host);
+  // FiLM table weights: all emb_layers.1 stacked row-wise in ResBlock creation order
+  {
+    film_.O = film_total_; film_.K = embed_dim_;
+    film_.w_off = ab.alloc(static_cast<size_t>(film_total_) * embed_dim_ * 4);
+    film_.b_off = ab.alloc(static_cast<size_t>(film_total_) * 4);
+    for (const auto& r : res_) {
+      const auto& w = P(r.pfx + ".emb_layers.1.weight").host;
+      const auto& b = P(r.pfx + ".emb_layers.1.bias").host;
+      std::memcpy(ab.at<float>(film_.w_off) + static_cast<size_t>(r.film_off) * embed_dim_, w.data(), w.size() * 4);
+      std::memcpy(ab.at<float>(film_.b_off) + r.film_off, b.data(), b.size() * 4);
+    }
+  }
+  in_conv_ = pack_conv("input_blocks.0.0.weight", "input_blocks.0.0.bias", in_ch_stem_, cfg_.in_channels, 64, 3, "", "", 0);
+  for (auto& r : res_) {
+    r.gn1 = pack_gn(r.pfx + ".in_layers.0", r.cin);
+    r.conv1 = pack_conv(r.pfx + ".in_layers.2.weight", r.pfx + ".in_layers.2.bias", r.cout, r.cin, r.cin, 3, "", "", 0);
+    r.gn2 = pack_gn(r.pfx + ".out_layers.0", r.cout);
+    r.conv2 = pack_conv(r.pfx + ".out_layers.3.weight", r.pfx + ".out_layers.3.bias", r.cout, r.cout, r.cout, 3,
+                        r.pfx + ".skip_connection.weight", r.pfx + ".skip_connection.bias", r.skip_conv ? r.cin : 0);
+  }
+  for (auto& a : attn_) {
+    a.gn = pack_gn(a.pfx + ".norm", a.C);
+    a.qkv = pack_conv(a.pfx + ".qkv.weight", a.pfx + ".qkv.bias", 3 * a.C, a.C, a.C, 1, "", "", 0);
+    a.proj = pack_conv(a.pfx + ".proj_out.weight", a.pfx + ".proj_out.bias", a.C, a.C, a.C, 1, "", "", 0);
+  }
+  out_gn_ = pack_gn("out.0", final_ch_);
+  out_conv_ = pack_conv("out.2.weight", "out.2.bias", cfg_.out_channels, final_ch_, final_ch_, 3, "", "", 0);
+
+  arena_bytes_ = (ab.buf.size() + 255) & ~size_t(255);
+  IVID_CHECK_CUDA(cudaMalloc(&arena_, arena_bytes_));
+  IVID_CHECK_CUDA(cudaMemcpy(arena_, ab.buf.data(), ab.buf.size(), cudaMemcpyHostToDevice));
+}
+
+Unet::~Unet() {
+  plans_.clear();
+  if (arena_) cudaFree(arena_);
+}
+
+// ==================================================================================================
+// execution plan
+// ==================================================================================================
+struct Plan {
+  int N = 0;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  double* stats_base = nullptr;
+  size_t stats_bytes = 0;
+  std::vector<std::function<void(cudaStream_t)>> ops;
+  std::vector<ConvLaunch*> convs;
+  std::vector<AttnLaunch*> attns;
+  // per-call inputs
+  const float* x = nullptr; int Nx = 0; ivid_cond_t cond{}; const int64_t* t = nullptr; const int64_t* classes = nullptr;
+  float* eps = nullptr;
+  const int* cond_stream_dev = nullptr;
+  ~Plan() {
+    for (auto* c : convs) conv_launch_destroy(c);
+    for (auto* a : attns) attn_launch_destroy(a);
+    if (ws) cudaFree(ws);
+  }
+};
+
+namespace {
+struct Act {          // fp32 NHWC residual-stream tensor with per-(n,channel) statistics
+  float* data = nullptr;
+  double* stats = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+struct Bump {
+  uint8_t* base; size_t off = 0;
+  explicit Bump(uint8_t* b) : base(b) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+}  // namespace
+
+Plan* Unet::get_plan(int N) {
+  for (auto& p : plans_) if (p->N == N) return p.get();
+  if (plans_.size() >= 3) plans_.erase(plans_.begin());
+  plans_.emplace_back(build_plan(N));
+  return plans_.back().get();
+}
+
+Plan* Unet::build_plan(int N) {
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->N = N;
+  Plan* pl = plan.get();
+  const int S = cfg_.image_size;
+  const int G = cfg_.num_groups;
+  const float eps = 1e-5f;
+  auto W8 = [&](size_t off) { return arena_ + off; };
+  auto Wf = [&](size_t off) { return reinterpret_cast<const float*>(arena_ + off); };
+
+  // ---- scratch maxima (walk the topology once for sizes) ----
+  size_t max_act16 = 0, max_raw16 = 0, max_f32 = 0, max_c = 0, max_qkv = 0;
+  {
+    int res = S;
+    auto upd_res = [&](const ResBlockDef& r) {
+      const int ro = r.mode == 1 ? res * 2 : (r.mode == 2 ? res / 2 : res);
+      max_act16 = std::max({max_act16, static_cast<size_t>(N) * ro * ro * r.cin, static_cast<size_t>(N) * ro * ro * r.cout});
+      max_raw16 = std::max(max_raw16, static_cast<size_t>(N) * res * res * r.cin);
+      max_f32 = std::max({max_f32, static_cast<size_t>(N) * ro * ro * r.cin, static_cast<size_t>(N) * ro * ro * r.cout});
+      max_c = std::max({max_c, static_cast<size_t>(r.cin), static_cast<size_t>(r.cout)});
+      res = ro;
+    };
+    for (const auto& b : blocks_)
+      for (const auto& l : b.layers) {
+        if (l.kind == 1) upd_res(res_[l.idx]);
+        else {
+          const auto& a = attn_[l.idx];
+          max_act16 = std::max(max_act16, static_cast<size_t>(N) * res * res * a.C);
+          max_qkv = std::max(max_qkv, static_cast<size_t>(N) * res * res * 3 * a.C);
+          max_c = std::max(max_c, static_cast<size_t>(a.C));
+        }
+      }
+    max_act16 = std::max(max_act16, static_cast<size_t>(N) * S * S * std::max(64, final_ch_));
+  }
+
+  // The same allocation sequence is run twice: once to size the workspace, once to build the launches.
+  auto layout = [&](uint8_t* base, bool create) -> size_t {
+    Bump bump(base);
+    // statistics arena is placed first so that its base is known while creating ops
+    // (sized generously: every tensor needs N*C*16 bytes; bound by total params walk below)
+    size_t stats_cap = 0;
+    {
+      int res = S;
+      stats_cap += static_cast<size_t>(N) * in_ch_stem_ * 16 + 1024;
+      for (const auto& b : blocks_)
+        for (const auto& l : b.layers) {
+          if (l.kind == 1) {
+            const auto& r = res_[l.idx];
+            stats_cap += 2 * (static_cast<size_t>(N) * r.cout * 16 + 1024);
+            res = r.mode == 1 ? res * 2 : (r.mode == 2 ? res / 2 : res);
+          } else {
+            stats_cap += static_cast<size_t>(N) * attn_[l.idx].C * 16 + 1024;
+          }
+        }
+    }
+    uint8_t* stats_base = static_cast<uint8_t*>(bump.take(stats_cap));
+    size_t soff = 0;
+    auto take_stats = [&](int C) -> double* {
+      const size_t o = soff;
+      soff += (static_cast<size_t>(N) * C * 16 + 255) & ~size_t(255);
+      return stats_base ? reinterpret_cast<double*>(stats_base + o) : nullptr;
+    };
+    auto stats_ptr = [&](const Act& a) { return a.stats; };
+    auto new_act = [&](int C, int H, int Wd) {
+      Act a; a.C = C; a.H = H; a.W = Wd;
+      a.data = static_cast<float*>(bump.take(static_cast<size_t>(N) * H * Wd * C * 4));
+      a.stats = take_stats(C);
+      return a;
+    };
+
+    // scratch
+    void* s_in = bump.take(static_cast<size_t>(N) * S * S * 64 * 2);
+    void* s_a1 = bump.take(max_act16 * 2);
+    void* s_a2 = bump.take(max_act16 * 2);
+    void* s_xh = bump.take(max_raw16 * 2);
+    float* s_xr = static_cast<float*>(bump.take(max_f32 * 4));
+    float* s_h = static_cast<float*>(bump.take(max_f32 * 4));
+    void* s_ab = bump.take(static_cast<size_t>(N) * max_c * 2 * 8);      // float2 per (n, c); 2x slack for concat
+    void* s_qkv = bump.take(std::max<size_t>(max_qkv, 1) * 2);
+    float* s_pe = static_cast<float*>(bump.take(static_cast<size_t>(N) * cfg_.model_channels * 4));
+    float* s_e1 = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
+    float* s_emb = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
+    float* s_film = static_cast<float*>(bump.take(static_cast<size_t>(N) * film_total_ * 4));
+
+    auto add_conv = [&](const ConvDesc& d) {
+      if (!create) return;
+      ConvLaunch* l = conv_launch_create(d);
+      pl->convs.push_back(l);
+      pl->ops.push_back([l](cudaStream_t s) { conv_launch_run(l, s); });
+    };
+    auto add_stats = [&](const Act& a) {
+      if (!create) return;
+      const float* x = a.data; double* st = stats_ptr(a);
+      const int HW = a.H * a.W, C = a.C;
+      pl->ops.push_back([=](cudaStream_t s) { launch_gn_stats(x, st, N, HW, C, s); });
+    };
+    auto add_coeff = [&](const Act& a0, const Act* a1, const GnW& g, int film_off) {
+      if (!create) return;
+      const double* st0 = stats_ptr(a0);
+      const double* st1 = a1 ? stats_ptr(*a1) : nullptr;
+      const int C0 = a0.C, C1 = a1 ? a1->C : 0, HW = a0.H * a0.W;
+      const float* gamma = Wf(g.g_off); const float* beta = Wf(g.b_off);
+      const float* film = film_off >= 0 ? s_film : nullptr;
+      const int fl = film_total_, fo = std::max(film_off, 0);
+      pl->ops.push_back([=](cudaStream_t s) {
+        launch_gn_coeff(st0, st1, C0, C1, N, G, HW, eps, gamma, beta, film, fl, fo, s_ab, s);
+      });
+    };
+    auto add_apply = [&](const GnApplyDesc& d) {
+      if (!create) return;
+      pl->ops.push_back([d](cudaStream_t s) { launch_gn_apply(d, s); });
+    };
+
+    // ---- embeddings ----
+    if (create) {
+      const float* freqs = Wf(freqs_off_);
+      const int half = cfg_.model_channels / 2, mc = cfg_.model_channels, E = embed_dim_;
+      const float *w1 = Wf(te1_.w_off), *b1 = Wf(te1_.b_off), *w2 = Wf(te2_.w_off), *b2 = Wf(te2_.b_off);
+      const float* lab = cfg_.num_classes > 0 ? Wf(label_off_) : nullptr;
+      const float *wf = Wf(film_.w_off), *bf = Wf(film_.b_off);
+      const int FT = film_total_;
+      pl->ops.push_back([=](cudaStream_t s) {
+        launch_posenc(pl->t, N, freqs, half, s_pe, N, s);
+        launch_linear(s_pe, w1, b1, s_e1, N, mc, E, 0, nullptr, nullptr, 1, s);
+        launch_linear(s_e1, w2, b2, s_emb, N, E, E, 1, pl->classes ? lab : nullptr, pl->classes, N, s);
+        launch_linear(s_emb, wf, bf, s_film, N, E, FT, 1, nullptr, nullptr, 1, s);
+      });
+    }
+
+    // ---- stem ----
+    if (create) {
+      const int Cin = cfg_.in_channels, HW = S * S;
+      pl->ops.push_back([=](cudaStream_t s) {
+        if (pl->cond.kind == 0) {
+          launch_pack_input(pl->x, s_in, N, pl->Nx, Cin, HW, s);
+        } else {
+          CondPackDesc cp;
+          cp.x = pl->x; cp.y = pl->cond.y_dev; cp.mask = pl->cond.mask_dev; cp.mask_rgb = pl->cond.mask_rgb_dev;
+          cp.noise = pl->cond.noise_dev; cp.out = s_in; cp.N = N; cp.Nx = pl->Nx; cp.H = S; cp.W = S;
+          cp.kind = pl->cond.kind; cp.seed = pl->cond.seed; cp.stream = pl->cond.stream_id; cp.stream_dev = pl->cond_stream_dev;
+          launch_cond_pack(cp, s);
+        }
+      });
+    }
+    Act cur = new_act(in_ch_stem_, S, S);
+    {
+      ConvDesc d;
+      d.act0 = s_in; d.C0 = 64; d.taps0 = 9;
+      d.weight = W8(in_conv_.w_off); d.cout_pad = in_conv_.cout_pad; d.cout = in_conv_.cout; d.bias = Wf(in_conv_.b_off);
+      d.out = cur.data; d.ldc = cur.C; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
+      add_conv(d);
+      add_stats(cur);
+    }
+    std::vector<Act> skips;
+    skips.push_back(cur);
+
+    auto run_res = [&](const ResBlockDef& r, const Act& x0, const Act* x1) -> Act {
+      const int Cin = x0.C + (x1 ? x1->C : 0);
+      IVID_REQUIRE(Cin == r.cin, "internal: ResBlock input width mismatch at " + r.pfx);
+      const int H = x0.H, Wd = x0.W;
+      const int Ho = r.mode == 1 ? H * 2 : (r.mode == 2 ? H / 2 : H);
+      const int Wo = r.mode == 1 ? Wd * 2 : (r.mode == 2 ? Wd / 2 : Wd);
+      const bool identity = !r.skip_conv;
+      const bool need_xr = identity && (r.mode != 0 || x1 != nullptr);   // resampled / concatenated identity skip
+      // GN1 + SiLU (+ resample) -> a1 ; raw fp16 copy for the 1x1 skip conv ; raw fp32 for resampled identity skip
+      add_coeff(x0, x1, r.gn1, -1);
+      GnApplyDesc g1;
+      g1.x0 = x0.data; g1.x1 = x1 ? x1->data : nullptr; g1.C0 = x0.C; g1.C1 = x1 ? x1->C : 0;
+      g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1; g1.ab = s_ab;
+      g1.out_act = s_a1; g1.out_raw16 = r.skip_conv ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
+      IVID_REQUIRE(!(r.skip_conv && r.mode != 0), "internal: up/down ResBlocks keep the channel count");
+      add_apply(g1);
+      // conv1 -> h (fp32) ; stats
+      Act h; h.C = r.cout; h.H = Ho; h.W = Wo; h.data = s_h;
+      h.stats = take_stats(r.cout);
+      {
+        ConvDesc d;
+        d.act0 = s_a1; d.C0 = r.cin; d.taps0 = 9;
+        d.weight = W8(r.conv1.w_off); d.cout_pad = r.conv1.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv1.b_off);
+        d.out = h.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
+        add_conv(d);
+        add_stats(h);
+      }
+      // GN2 * (1+scale) + shift, SiLU -> a2
+      add_coeff(h, nullptr, r.gn2, r.film_off);
+      GnApplyDesc g2;
+      g2.x0 = h.data; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1; g2.ab = s_ab;
+      g2.out_act = s_a2;
+      add_apply(g2);
+      // conv2 (+ 1x1 skip as extra K) + residual -> out
+      Act out = new_act(r.cout, Ho, Wo);
+      {
+        ConvDesc d;
+        d.act0 = s_a2; d.C0 = r.cout; d.taps0 = 9;
+        if (r.skip_conv) { d.act1 = s_xh; d.C1 = r.cin; d.taps1 = 1; }
+        d.weight = W8(r.conv2.w_off); d.cout_pad = r.conv2.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv2.b_off);
+        if (identity) { d.residual = need_xr ? s_xr : x0.data; d.ldr = r.cout; }
+        d.out = out.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
+        add_conv(d);
+        add_stats(out);
+      }
+      return out;
+    };
+    auto run_attn = [&](const AttnBlockDef& a, const Act& x) -> Act {
+      IVID_REQUIRE(x.C == a.C, "internal: attention width mismatch at " + a.pfx);
+      const int T = x.H * x.W;
+      add_coeff(x, nullptr, a.gn, -1);
+      GnApplyDesc g;
+      g.x0 = x.data; g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.ab = s_ab; g.out_act = s_a1;
+      add_apply(g);
+      {
+        ConvDesc d;
+        d.act0 = s_a1; d.C0 = a.C; d.taps0 = 1;
+        d.weight = W8(a.qkv.w_off); d.cout_pad = a.qkv.cout_pad; d.cout = 3 * a.C; d.bias = Wf(a.qkv.b_off);
+        d.out = s_qkv; d.ldc = 3 * a.C; d.out_mode = 1; d.N = N; d.H = x.H; d.W = x.W;
+        add_conv(d);
+      }
+      if (create) {
+        AttnLaunch* l = attn_launch_create(s_qkv, N, T, a.C, s_a2);
+        pl->attns.push_back(l);
+        pl->ops.push_back([l](cudaStream_t s) { attn_launch_run(l, s); });
+      }
+      Act out = new_act(a.C, x.H, x.W);
+      {
+        ConvDesc d;
+        d.act0 = s_a2; d.C0 = a.C; d.taps0 = 1;
+        d.weight = W8(a.proj.w_off); d.cout_pad = a.proj.cout_pad; d.cout = a.C; d.bias = Wf(a.proj.b_off);
+        d.residual = x.data; d.ldr = a.C;
+        d.out = out.data; d.ldc = a.C; d.out_mode = 0; d.N = N; d.H = x.H; d.W = x.W;
+        add_conv(d);
+        add_stats(out);
+      }
+      return out;
+    };
+
+    for (size_t bi = 1; bi < blocks_.size(); ++bi) {
+      const BlockDef& b = blocks_[bi];
+      bool first = true;
+      for (const auto& l : b.layers) {
+        if (l.kind == 1) {
+          if (b.is_output && first) {
+            Act sk = skips.back();
+            skips.pop_back();
+            cur = run_res(res_[l.idx], cur, &sk);
+          } else {
+            cur = run_res(res_[l.idx], cur, nullptr);
+          }
+        } else {
+          cur = run_attn(attn_[l.idx], cur);
+        }
+        first = false;
+      }
+      if (b.is_input) skips.push_back(cur);
+    }
+    IVID_REQUIRE(skips.empty(), "internal: skip stack not consumed");
+
+    // ---- output head: GN + SiLU + conv3x3 -> eps (fp32 NCHW) ----
+    add_coeff(cur, nullptr, out_gn_, -1);
+    GnApplyDesc go;
+    go.x0 = cur.data; go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.ab = s_ab; go.out_act = s_a1;
+    add_apply(go);
+    if (create) {
+      ConvDesc d;
+      d.act0 = s_a1; d.C0 = cur.C; d.taps0 = 9;
+      d.weight = W8(out_conv_.w_off); d.cout_pad = out_conv_.cout_pad; d.cout = cfg_.out_channels; d.bias = Wf(out_conv_.b_off);
+      d.out = nullptr; d.ldc = 0; d.out_mode = 2; d.N = N; d.H = S; d.W = S;
+      ConvLaunch* l = conv_launch_create(d);
+      pl->convs.push_back(l);
+      // eps pointer is a per-call input: patched through the plan at run time
+      pl->ops.push_back([l, pl](cudaStream_t s) { conv_launch_run_out(l, pl->eps, s); });
+    }
+    if (create) {
+      pl->stats_base = reinterpret_cast<double*>(stats_base);
+      pl->stats_bytes = soff;
+      IVID_REQUIRE(soff <= stats_cap, "internal: statistics arena overflow");
+    }
+    return bump.off;
+  };
+
+  const size_t total = layout(nullptr, false);
+  IVID_CHECK_CUDA(cudaMalloc(&pl->ws, total + 4096));
+  pl->ws_bytes = total;
+  layout(pl->ws, true);
+  return plan.release();
+}
+
+void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_t* t, const int64_t* classes, float* eps,
+                   int N, cudaStream_t stream) {
+  if (!finalized()) throw Error(kErrState, "AdmUnet2d: forward before .cuda()/finalize");
+  IVID_REQUIRE(N >= 1 && Nx >= 1 && N % Nx == 0, "forward: N must be a positive multiple of Nx");
+  // reference: "this model is not class-conditioned" (adm.py:540)
+  IVID_REQUIRE(classes == nullptr || cfg_.num_classes > 0, "this model is not class-conditioned");
+  IVID_CHECK_CUDA(cudaSetDevice(device_));
+  Plan* pl = get_plan(N);
+  pl->x = x; pl->Nx = Nx; pl->t = t; pl->classes = classes; pl->eps = eps;
+  if (cond) pl->cond = *cond; else pl->cond = ivid_cond_t{};
+  const int expect_in = pl->cond.kind == 1 ? (pl->cond.mask_rgb_dev ? 10 : 9) : (pl->cond.kind == 2 ? 8 : cfg_.in_channels);
+  IVID_REQUIRE(expect_in == cfg_.in_channels, "forward: conditional inputs do not match the model's in_channels");
+  IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
+  for (auto& op : pl->ops) op(stream);
+}
+
+}  // namespace ivid
