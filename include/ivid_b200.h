@@ -62,6 +62,12 @@ int ivid_unet_weight_arena(const ivid_unet_t* h, void** dev_ptr, uint64_t* bytes
 int ivid_unet_forward(ivid_unet_t* h, const float* x_dev, int Nx, const int64_t* t_dev, const int64_t* classes_dev,
                       float* eps_dev, int N, void* stream);
 
+/* Profiling aid (bench.py roofline): between begin/end every kernel launch of ivid_unet_forward is bracketed by CUDA
+ * events on the launching stream; end returns JSON {"kernel family": {"launches","ms","flops","bytes"}} where flops /
+ * bytes are the ALGORITHMIC figures of DESIGN.md.  Forwards issued while profiling synchronise the stream. */
+int ivid_unet_profile_begin(ivid_unet_t* h);
+int ivid_unet_profile_end(ivid_unet_t* h, char* json_out, int capacity);
+
 /* Conditional inputs assembled on the fly (never materialised in fp32):
  *   kind 1: InpaintCFG.make_cond_inputs (frameworks/inpaint_cfg.py:24-49): cat[x, mask_rgb, y_rgb*m_rgb+z*(1-m_rgb),
  *           y_d*m+z*(1-m), m];  noise_dev = injected z [Nx,4,H,W] or NULL (in-kernel Philox(seed, stream)).

@@ -115,6 +115,18 @@ int ivid_unet_forward_cond(ivid_unet_t* h, const float* x_dev, int Nx, const ivi
   });
 }
 
+int ivid_unet_profile_begin(ivid_unet_t* h) {
+  return guarded([&] { IVID_NOT_NULL(h); h->impl->profile_begin(); });
+}
+int ivid_unet_profile_end(ivid_unet_t* h, char* json_out, int capacity) {
+  return guarded([&] {
+    IVID_NOT_NULL(h); IVID_NOT_NULL(json_out);
+    const std::string js = h->impl->profile_end();
+    IVID_REQUIRE(static_cast<int>(js.size()) < capacity, "profile buffer too small");
+    std::memcpy(json_out, js.c_str(), js.size() + 1);
+  });
+}
+
 int ivid_sampler_create(const double* betas, int timesteps, ivid_sampler_t** out) {
   return guarded([&] {
     IVID_NOT_NULL(betas); IVID_NOT_NULL(out);

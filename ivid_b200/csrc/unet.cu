@@ -348,7 +348,21 @@ struct Plan {
   size_t ws_bytes = 0;
   double* stats_base = nullptr;
   size_t stats_bytes = 0;
-  std::vector<std::function<void(cudaStream_t)>> ops;
+  struct OpRec {
+    std::function<void(cudaStream_t)> fn;
+    const char* label;      // kernel family (profile aggregation key)
+    double flops;           // algorithmic FLOPs of this launch (tensor-core ops)
+    double bytes;           // algorithmic HBM bytes of this launch (memory-bound ops)
+  };
+  struct OpList {
+    std::vector<OpRec> v;
+    const char* label = "other"; double flops = 0, bytes = 0;     // metadata of the next push
+    void tag(const char* l, double f, double b) { label = l; flops = f; bytes = b; }
+    void push_back(std::function<void(cudaStream_t)> fn) {
+      v.push_back(OpRec{std::move(fn), label, flops, bytes});
+      label = "other"; flops = 0; bytes = 0;
+    }
+  } ops;
   std::vector<ConvLaunch*> convs;
   std::vector<AttnLaunch*> attns;
   // per-call inputs
@@ -475,12 +489,19 @@ Plan* Unet::build_plan(int N) {
       if (!create) return;
       ConvLaunch* l = conv_launch_create(d);
       pl->convs.push_back(l);
+      const double K = static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0);
+      const double M = static_cast<double>(d.N) * d.H * d.W;
+      static const char* names[] = {"conv_gemm<16>", "conv_gemm<64>", "conv_gemm<128>", "conv_gemm<256>"};
+      const int bn = conv_pick_bn(d.cout_pad);
+      pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * d.cout,
+                  M * K / (d.taps0 == 9 ? 9.0 : 1.0) * 2 + M * d.cout * (d.out_mode == 1 ? 2 : 4) + K * d.cout_pad * 2);
       pl->ops.push_back([l](cudaStream_t s) { conv_launch_run(l, s); });
     };
     auto add_stats = [&](const Act& a) {
       if (!create) return;
       const float* x = a.data; double* st = stats_ptr(a);
       const int HW = a.H * a.W, C = a.C;
+      pl->ops.tag("gn_stats", 0, static_cast<double>(N) * HW * C * 4);
       pl->ops.push_back([=](cudaStream_t s) { launch_gn_stats(x, st, N, HW, C, s); });
     };
     auto add_coeff = [&](const Act& a0, const Act* a1, const GnW& g, int film_off) {
@@ -491,12 +512,19 @@ Plan* Unet::build_plan(int N) {
       const float* gamma = Wf(g.g_off); const float* beta = Wf(g.b_off);
       const float* film = film_off >= 0 ? s_film : nullptr;
       const int fl = film_total_, fo = std::max(film_off, 0);
+      pl->ops.tag("gn_coeff", 0, static_cast<double>(N) * (C0 + C1) * 24);
       pl->ops.push_back([=](cudaStream_t s) {
         launch_gn_coeff(st0, st1, C0, C1, N, G, HW, eps, gamma, beta, film, fl, fo, s_ab, s);
       });
     };
     auto add_apply = [&](const GnApplyDesc& d) {
       if (!create) return;
+      {
+        const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
+        const double in_el = static_cast<double>(d.N) * d.H * d.W * (d.C0 + d.C1);
+        const double out_el = static_cast<double>(d.N) * Ho * Ho * (d.C0 + d.C1);
+        pl->ops.tag("gn_apply", 0, in_el * 4 + out_el * 2 + (d.out_raw16 ? out_el * 2 : 0) + (d.out_raw32 ? out_el * 4 : 0));
+      }
       pl->ops.push_back([d](cudaStream_t s) { launch_gn_apply(d, s); });
     };
 
@@ -508,6 +536,7 @@ Plan* Unet::build_plan(int N) {
       const float* lab = cfg_.num_classes > 0 ? Wf(label_off_) : nullptr;
       const float *wf = Wf(film_.w_off), *bf = Wf(film_.b_off);
       const int FT = film_total_;
+      pl->ops.tag("embed", 2.0 * N * E * (mc + E + FT), 4.0 * E * (mc + E + FT));
       pl->ops.push_back([=](cudaStream_t s) {
         launch_posenc(pl->t, N, freqs, half, s_pe, N, s);
         launch_linear(s_pe, w1, b1, s_e1, N, mc, E, 0, nullptr, nullptr, 1, s);
@@ -519,6 +548,7 @@ Plan* Unet::build_plan(int N) {
     // ---- stem ----
     if (create) {
       const int Cin = cfg_.in_channels, HW = S * S;
+      pl->ops.tag("pack_input", 0, static_cast<double>(N) * HW * (Cin * 4 + 128));
       pl->ops.push_back([=](cudaStream_t s) {
         if (pl->cond.kind == 0) {
           launch_pack_input(pl->x, s_in, N, pl->Nx, Cin, HW, s);
@@ -607,6 +637,7 @@ Plan* Unet::build_plan(int N) {
       if (create) {
         AttnLaunch* l = attn_launch_create(s_qkv, N, T, a.C, s_a2);
         pl->attns.push_back(l);
+        pl->ops.tag("attention", 4.0 * N * (a.C / 64) * static_cast<double>(T) * T * 64, static_cast<double>(N) * T * a.C * 8);
         pl->ops.push_back([l](cudaStream_t s) { attn_launch_run(l, s); });
       }
       Act out = new_act(a.C, x.H, x.W);
@@ -656,6 +687,8 @@ Plan* Unet::build_plan(int N) {
       ConvLaunch* l = conv_launch_create(d);
       pl->convs.push_back(l);
       // eps pointer is a per-call input: patched through the plan at run time
+      pl->ops.tag("conv_gemm<16>", 2.0 * N * S * S * 9.0 * cur.C * cfg_.out_channels,
+                  static_cast<double>(N) * S * S * (cur.C * 2 + cfg_.out_channels * 4));
       pl->ops.push_back([l, pl](cudaStream_t s) { conv_launch_run_out(l, pl->eps, s); });
     }
     if (create) {
@@ -686,7 +719,43 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   const int expect_in = pl->cond.kind == 1 ? (pl->cond.mask_rgb_dev ? 10 : 9) : (pl->cond.kind == 2 ? 8 : cfg_.in_channels);
   IVID_REQUIRE(expect_in == cfg_.in_channels, "forward: conditional inputs do not match the model's in_channels");
   IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
-  for (auto& op : pl->ops) op(stream);
+  if (!profile_) {
+    for (auto& op : pl->ops.v) op.fn(stream);
+    return;
+  }
+  // profiling pass: every launch bracketed by CUDA events on the launching stream (serialised; shares, not absolutes)
+  std::vector<cudaEvent_t> ev(pl->ops.v.size() + 1);
+  for (auto& e : ev) IVID_CHECK_CUDA(cudaEventCreate(&e));
+  IVID_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < pl->ops.v.size(); ++i) {
+    pl->ops.v[i].fn(stream);
+    IVID_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
+  }
+  IVID_CHECK_CUDA(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < pl->ops.v.size(); ++i) {
+    float ms = 0.f;
+    IVID_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    auto& agg = profile_acc_[pl->ops.v[i].label];
+    agg.launches += 1; agg.ms += ms; agg.flops += pl->ops.v[i].flops; agg.bytes += pl->ops.v[i].bytes;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+}
+
+void Unet::profile_begin() { profile_ = true; profile_acc_.clear(); }
+std::string Unet::profile_end() {
+  profile_ = false;
+  std::string js = "{";
+  bool first = true;
+  for (const auto& kv : profile_acc_) {
+    if (!first) js += ", ";
+    first = false;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "\"%s\": {\"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", kv.first.c_str(),
+             kv.second.launches, kv.second.ms, kv.second.flops, kv.second.bytes);
+    js += buf;
+  }
+  js += "}";
+  return js;
 }
 
 }  // namespace ivid

@@ -80,6 +80,9 @@ class Unet {
   // forward over a batch of N samples; x rows are read modulo Nx (CFG halves share x)
   void forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_t* t, const int64_t* classes, float* eps,
                int N, cudaStream_t stream);
+  // per-kernel-family timing of the forwards issued between begin/end (CUDA events around every launch)
+  void profile_begin();
+  std::string profile_end();    // JSON: {"label": {"launches", "ms", "flops", "bytes"}, ...}
 
  private:
   void build_topology();
@@ -108,6 +111,9 @@ class Unet {
   size_t arena_bytes_ = 0;
   int device_ = -1;
 
+  struct ProfAgg { int launches = 0; double ms = 0, flops = 0, bytes = 0; };
+  bool profile_ = false;
+  std::map<std::string, ProfAgg> profile_acc_;
   std::vector<std::unique_ptr<Plan>> plans_;
   friend struct Plan;
 };

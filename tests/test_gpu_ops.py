@@ -1,0 +1,123 @@
+"""GPU parity of the individual sm_100a kernels against fp32 torch on the CPU (through the op-level C ABI).
+
+Tolerances: tensor-core operands are fp16 (10-bit mantissa, like the TF32 path the reference's cuDNN convs took on
+A100) with fp32 accumulation, so a single conv/GEMM is compared at 2e-3 relative L2 against the fp32 result of the SAME
+fp16-rounded operands at 2e-5 (accumulation-order only)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _t(rng, *shape, scale=1.0):
+    return torch.from_numpy((rng.standard_normal(shape) * scale).astype(np.float32))
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k
+    (2, 16, 16, 64, 64, 3),
+    (1, 32, 32, 128, 256, 3),
+    (3, 8, 8, 256, 128, 3),      # TN=2 tiles with odd batch (batch tail masked)
+    (2, 16, 16, 192, 384, 1),    # 1x1, BN=128
+    (1, 4, 4, 64, 64, 3),        # tiny spatial: TN=8 with N=1
+    (2, 64, 64, 64, 16, 3),      # narrow Cout (BN=16 path, output head shape)
+    (1, 128, 128, 256, 256, 3),  # the dominant shape of the large model
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", CONV_CASES)
+def test_conv_matches_torch(N, H, W, Cin, Cout, k):
+    rng = _rng(hash((N, H, W, Cin, Cout, k)) % 2**31)
+    x = _t(rng, N, Cin, H, W)
+    w = _t(rng, Cout, Cin, k, k, scale=1 / math.sqrt(Cin * k * k))
+    b = _t(rng, Cout, scale=0.1)
+    xh = x.half()
+    ref16 = F.conv2d(xh.float(), w.half().float(), b, padding=k // 2)       # same rounded operands, fp32 math
+    ref32 = F.conv2d(x, w, b, padding=k // 2)
+    out = G.conv2d(xh.permute(0, 2, 3, 1).contiguous().cuda(), w, b, k)
+    got = out.permute(0, 3, 1, 2).cpu()
+    r16 = G.report(f"conv N{N} {H}x{W} {Cin}->{Cout} k{k} (vs fp16-rounded operands)", got, ref16)
+    r32 = G.report(f"conv N{N} {H}x{W} {Cin}->{Cout} k{k} (vs fp32)", got, ref32)
+    assert r16 < 2e-5
+    assert r32 < 2e-3
+
+
+def test_conv_skip_segment_residual_and_fp16_out():
+    """out_layers conv + 1x1 skip conv as extra K slabs (ResBlock tail, adm.py:222), identity residual, fp16 output."""
+    rng = _rng(5)
+    N, H, W, C, Cx = 2, 16, 16, 128, 192
+    a = _t(rng, N, C, H, W); x = _t(rng, N, Cx, H, W)
+    w = _t(rng, C, C, 3, 3, scale=1 / math.sqrt(9 * C)); b = _t(rng, C, scale=0.1)
+    ws = _t(rng, C, Cx, 1, 1, scale=1 / math.sqrt(Cx)); bs = _t(rng, C, scale=0.1)
+    ref = F.conv2d(a.half().float(), w.half().float(), b, padding=1) + F.conv2d(x.half().float(), ws.half().float(), bs)
+    out = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3,
+                   act2=x.half().permute(0, 2, 3, 1).contiguous().cuda(), w2=ws, b2=bs)
+    assert G.report("conv3x3 + 1x1 skip segment", out.permute(0, 3, 1, 2), ref) < 2e-5
+    res = _t(rng, N, C, H, W)
+    ref2 = F.conv2d(a.half().float(), w.half().float(), b, padding=1) + res
+    out2 = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3, residual=res.permute(0, 2, 3, 1).contiguous().cuda())
+    assert G.report("conv3x3 + identity residual", out2.permute(0, 3, 1, 2), ref2) < 2e-5
+    out3 = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3, out_fp16=True)
+    assert G.report("conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), F.conv2d(a.half().float(), w.half().float(), b, padding=1)) < 5e-4
+
+
+GN_CASES = [
+    # N, H, W, C0, C1, groups, silu, mode, film
+    (2, 16, 16, 64, 0, 32, True, 0, False),
+    (2, 16, 16, 128, 0, 32, True, 0, True),
+    (3, 8, 8, 1024, 768, 32, True, 0, False),    # 1792 = 1024 (+) 768: 56 channels / group straddles the seam
+    (2, 16, 16, 512, 256, 32, True, 0, False),   # 768 = 512 (+) 256: 24 / group straddles
+    (2, 16, 16, 128, 0, 32, True, 1, False),     # nearest 2x upsample after GN+SiLU
+    (2, 16, 16, 128, 0, 32, True, 2, False),     # 2x2 average pool after GN+SiLU
+    (1, 32, 32, 512, 0, 32, False, 0, False),    # attention norm (no SiLU)
+]
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,groups,silu,mode,film", GN_CASES)
+def test_group_norm_matches_torch(N, H, W, C0, C1, groups, silu, mode, film):
+    rng = _rng(hash((N, H, W, C0, C1, mode)) % 2**31)
+    C = C0 + C1
+    x0 = _t(rng, N, C0, H, W) * 1.7 + 0.3
+    x1 = (_t(rng, N, C1, H, W) * 0.6 - 0.2) if C1 else None
+    gamma = 1 + 0.1 * _t(rng, C); beta = 0.1 * _t(rng, C)
+    x = torch.cat([x0, x1], 1) if C1 else x0
+    y = F.group_norm(x, groups, gamma, beta, 1e-5)
+    fl = None
+    if film:
+        fl = 0.3 * _t(rng, N, 2 * C)
+        y = y * (1 + fl[:, :C, None, None]) + fl[:, C:, None, None]
+    if silu:
+        y = F.silu(y)
+    if mode == 1:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    elif mode == 2:
+        y = F.avg_pool2d(y, 2)
+    out = G.group_norm(x0.permute(0, 2, 3, 1).contiguous().cuda(), x1.permute(0, 2, 3, 1).contiguous().cuda() if C1 else None,
+                       groups, gamma, beta, fl.cuda() if film else None, silu, mode)
+    r = G.report(f"group_norm N{N} {H}x{W} C{C0}+{C1} silu{silu} mode{mode} film{film}", out.float().permute(0, 3, 1, 2), y)
+    assert r < 6e-4     # output is rounded to fp16 (2^-11 relative)
+
+
+@pytest.mark.parametrize("N,T,C", [(2, 64, 128), (1, 256, 192), (2, 1024, 128), (1, 4096, 64)])
+def test_attention_matches_torch(N, T, C):
+    rng = _rng(T + C)
+    qkv = _t(rng, N, 3 * C, T)                     # reference layout [N, 3C, T]
+    qh = qkv.half()
+    heads = C // 64
+    q, k, v = qh.float().reshape(N * heads, 3 * 64, T).split(64, dim=1)
+    s = 1 / math.sqrt(math.sqrt(64))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(N, C, T)
+    out = G.attention(qh.permute(0, 2, 1).contiguous().cuda(), C)     # [N, T, 3C]
+    r = G.report(f"attention N{N} T{T} C{C}", out.float().permute(0, 2, 1), ref)
+    assert r < 2e-3
