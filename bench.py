@@ -98,7 +98,20 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_step_seconds(steps, warmup, budget_s=150.0):
     from oracle import sampler_ref, unet_ref
-    cores = os.cpu_count() or 1
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # use the thread count that is actually fastest on this host (oversubscribed SMT threads slow oneDNN down)
+    probe_x = torch.randn(1, 256, 128, 128)
+    probe_w = torch.randn(256, 256, 3, 3)
+    best, cores = None, 1
+    for nt in sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)}):
+        torch.set_num_threads(nt)
+        torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, nt
     torch.set_num_threads(cores)
     sd = unet_ref.make_synthetic_state_dict(LARGE_CFG, seed=1234)
     tb = sampler_ref.Tables(sampler_ref.get_betas("linear", 1000))

@@ -195,7 +195,7 @@ void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float
 
 void launch_linear(const float* in, const float* W, const float* bias, float* out, int N, int K, int O, int silu_in,
                    const float* label_emb, const int64_t* classes, int Ncls, cudaStream_t s) {
-  dim3 grid((O + 7) / 8, (N + 31) / 32);
+  dim3 grid((O + 63) / 64, (N + 31) / 32);
   linear_rows_kernel<<<grid, 256, 0, s>>>(in, W, bias, out, N, K, O, silu_in, label_emb, classes, Ncls);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
