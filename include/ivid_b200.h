@@ -135,6 +135,56 @@ int ivid_sampler_run(ivid_sampler_t* s, ivid_unet_t* unet, float* x_inout_dev, i
                      float* traj_x0_dev, float* traj_xt_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * RGBD novel-view warp — replaces rgbd_3d.utils.{linearize_depth, depth_to_mesh, aggregate_conditions, project_depth,
+ * depth_edge} (rgbd_3d/utils.py:38-67,144-260,311-332,420-477) and rgbd_3d.AggregationRenderer with its GLSL shaders
+ * (rgbd_3d/moderngl_renderer.py:151-340, shaders/aggregation.{vsh,fsh,csh}, clear.csh).  All source views of a batch of
+ * samples stay resident on the device; modelview matrices are float32[16] row-major in mathematical orientation
+ * (p_cam = M * p_world), what glm.lookAt produces (inference/sample.py:304-336).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ivid_warp ivid_warp_t;
+typedef struct {
+  double fov_deg;   /* sample.py:258 --fov 45 */
+  double near;      /* sample.py:259 --near 0.6  (z-buffer depth <-> linear depth) */
+  double far;       /* sample.py:260 --far 5 */
+  double atol;      /* sample.py:261 */
+  double rtol;      /* sample.py:262 */
+  int erode_rgb;    /* sample.py:263 */
+} ivid_warp_params_t;
+
+/* [AggregationRenderer(render_size, image_size, near, far) for _ in range(batch)]  (sample.py:50) */
+int ivid_warp_create(int image_size, int render_size, int max_views, int batch, double near, double far, int device,
+                     ivid_warp_t** out);
+int ivid_warp_destroy(ivid_warp_t* w);
+int ivid_warp_reset(ivid_warp_t* w);                       /* start a new batch of samples: forget all source views */
+int ivid_warp_num_views(const ivid_warp_t* w, int* n);
+/* For every sample of the batch: colors.append(rgb); meshes.append(depth_to_mesh(linearize_depth(depth, near, far),
+ * padding='frustum', fov, modelview, atol, rtol, erode_rgb, cal_normal=True))   (sample.py:83,126-139).
+ * rgbd_dev: fp32 [batch,4,H,W] sampler output in [-1,1]; modelviews_host: [batch][16] (or one shared matrix). */
+int ivid_warp_add_view(ivid_warp_t* w, const float* rgbd_dev, const float* modelviews_host, int shared_modelview,
+                       const ivid_warp_params_t* params, void* stream);
+/* rgbd_3d.utils.depth_to_mesh(depth, padding='frustum', cal_normal=True, ...) with numpy in/out (utils.py:144-260):
+ * lin_depth_host [H][W] float32 linearised depth -> vertex buffer [(H+2)^2][9] and faces [2*(H+1)^2][3] on the host. */
+int ivid_warp_mesh_from_depth(ivid_warp_t* w, const float* lin_depth_host, const float* modelview_host,
+                              const ivid_warp_params_t* params, float* verts_host, uint32_t* faces_host, void* stream);
+/* External meshes (numpy-facing mirror of AggregationRenderer.render, tests): vertex buffer [(H+2)^2][9] float32 =
+ * position, normal, uv, flag (moderngl_renderer.py:284-289), faces [2*(H+1)^2][3] uint32, colour texture [H][W][3]. */
+int ivid_warp_set_mesh(ivid_warp_t* w, int sample, int view, const float* verts_host, const uint32_t* faces_host,
+                       const float* color_host, const float* modelview_host);
+int ivid_warp_get_mesh(ivid_warp_t* w, int sample, int view, float* verts_host, uint32_t* faces_host, float* color_host);
+/* AggregationRenderer.render(meshes, colors, modelview, fov, is_autoregressive=True) for one target view per sample.
+ * Device outputs at render_size S (any may be NULL): color [batch,S,S,3], depth [batch,S,S], masks [batch,S,S] (0/1). */
+int ivid_warp_render(ivid_warp_t* w, const float* target_mv_host, int shared_modelview, double fov_deg, float* color_dev,
+                     float* depth_dev, float* mask_color_dev, float* mask_depth_dev, void* stream);
+/* aggregate_conditions(...) (utils.py:420-477): cond_dev fp32 [batch,7,H,W] = color(3), depth, mask, mask_rgb,
+ * depth_convex, all in [0,1] exactly like the numpy dict the reference returns. */
+int ivid_warp_aggregate(ivid_warp_t* w, const float* target_mv_host, int shared_modelview, const ivid_warp_params_t* params,
+                        float* cond_dev, void* stream);
+/* The post-filter half of aggregate_conditions alone (LANCZOS on 8-bit colour, depth point sample + project_depth,
+ * 7-of-9 votes, depth_edge, erosion) on caller-provided raw renders. */
+int ivid_warp_postfilter(ivid_warp_t* w, const float* color_dev, const float* depth_dev, const float* mask_color_dev,
+                         const float* mask_depth_dev, const ivid_warp_params_t* params, float* cond_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Operator-level entry points (unit parity tests, profiling): the kernels the UNet is assembled from.
  * ------------------------------------------------------------------------------------------------------------------ */
 

@@ -54,6 +54,11 @@ class StepArgsT(Structure):
     ]
 
 
+class WarpParamsT(Structure):
+    _fields_ = [("fov_deg", c_double), ("near", c_double), ("far", c_double), ("atol", c_double), ("rtol", c_double),
+                ("erode_rgb", c_int)]
+
+
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against the header
 SIGNATURES = {
     "ivid_last_error": (c_char_p, []),
@@ -80,11 +85,17 @@ SIGNATURES = {
     "ivid_op_group_norm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ivid_op_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "ivid_warp_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "ivid_warp_create": (c_int, [c_int, c_int, c_int, c_int, c_double, c_double, c_int, POINTER(c_void_p)]),
     "ivid_warp_destroy": (c_int, [c_void_p]),
     "ivid_warp_reset": (c_int, [c_void_p]),
-    "ivid_warp_add_view": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p]),
-    "ivid_warp_aggregate": (c_int, [c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p]),
+    "ivid_warp_num_views": (c_int, [c_void_p, POINTER(c_int)]),
+    "ivid_warp_add_view": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(WarpParamsT), c_void_p]),
+    "ivid_warp_mesh_from_depth": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(WarpParamsT), c_void_p, c_void_p, c_void_p]),
+    "ivid_warp_set_mesh": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ivid_warp_get_mesh": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ivid_warp_render": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ivid_warp_aggregate": (c_int, [c_void_p, c_void_p, c_int, POINTER(WarpParamsT), c_void_p, c_void_p]),
+    "ivid_warp_postfilter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(WarpParamsT), c_void_p, c_void_p]),
 }
 
 _lib = None

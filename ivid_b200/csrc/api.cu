@@ -15,6 +15,7 @@ struct ivid_unet { std::unique_ptr<Unet> impl; };
 struct ivid_sampler { std::unique_ptr<Sampler> impl; };
 
 static thread_local std::string g_last_error;
+namespace ivid { void set_last_error(const std::string& msg) { g_last_error = msg; } }
 
 template <class F>
 static int guarded(F&& f) {

@@ -1,0 +1,172 @@
+"""AggregationRenderer — host-side mirror of rgbd_3d.AggregationRenderer (reference moderngl_renderer.py:151-340) on
+the CUDA rasteriser behind the C ABI (no OpenGL / EGL), plus DeviceWarp: the device-resident multiview warp used by
+the sampling loop (all source views of a batch stay in HBM; no per-view host round trips).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils import edict
+from .glm_compat import as_matrix
+
+__all__ = ["AggregationRenderer", "DeviceWarp", "warp_params"]
+
+
+def warp_params(fov=45, near=0.5, far=100, atol=0.02, rtol=0.02, erode_rgb=2) -> _lib.WarpParamsT:
+    p = _lib.WarpParamsT()
+    p.fov_deg, p.near, p.far = float(fov), float(near), float(far)
+    p.atol = 0.0 if atol is None else float(atol)
+    p.rtol = 0.0 if rtol is None else float(rtol)
+    p.erode_rgb = int(erode_rgb or 0)
+    return p
+
+
+def _mv(m) -> np.ndarray:
+    return np.ascontiguousarray(as_matrix(m), dtype=np.float32)
+
+
+class _Native:
+    def __init__(self, image_size, render_size, max_views, batch, near, far, device):
+        assert torch.cuda.is_available(), "ivid_b200.rgbd_3d runs on CUDA only (no CPU path)"
+        self.image_size, self.render_size, self.max_views, self.batch = image_size, render_size, max_views, batch
+        self.near, self.far, self.device = near, far, device
+        self._handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().ivid_warp_create(image_size, render_size, max_views, batch, float(near), float(far), int(device),
+                                               ctypes.byref(self._handle)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().ivid_warp_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return _lib.cur_stream(torch.device("cuda", self.device))
+
+
+class AggregationRenderer(_Native):
+    """Renderer of 3D meshes with multi-view aggregation (reference moderngl_renderer.py:151).
+
+    Args (as the reference): render_size, image_size, near, far, device, max_views.
+    """
+
+    def __init__(self, render_size=128, image_size=128, near=0.01, far=200.0, device=0, max_views=27):
+        # one spare slot is used by utils.depth_to_mesh as scratch
+        super().__init__(image_size, render_size, max_views + 1, 1, near, far, device)
+        self._uploaded = 0
+
+    def render(self, meshes, colors, modelview, fov=45.0, is_autoregressive=False, verbose=False, tqdm_args={}):
+        """Render the aggregated view(s) (reference moderngl_renderer.py:260-340).  numpy HWC in / out."""
+        L = _lib.lib()
+        for i, mesh in enumerate(meshes):
+            if is_autoregressive and i != len(meshes) - 1:
+                continue      # earlier views were uploaded by earlier calls (moderngl_renderer.py:281-283)
+            v = mesh.vertices if hasattr(mesh, "vertices") else mesh["vertices"]
+            vb = np.ascontiguousarray(np.concatenate([v["position"], v["normal"], v["uv"], v["flag"]], axis=-1).astype(np.float32))
+            faces = np.ascontiguousarray((mesh.faces if hasattr(mesh, "faces") else mesh["faces"]).astype(np.uint32))
+            col = np.ascontiguousarray(colors[i].astype(np.float32))
+            mv = _mv(mesh.modelview if hasattr(mesh, "modelview") else mesh["modelview"])
+            _lib.check(L.ivid_warp_set_mesh(self._handle, 0, i, vb.ctypes.data, faces.ctypes.data, col.ctypes.data, mv.ctypes.data))
+        # the native view count is max(uploaded)+1; make it match len(meshes)
+        targets = modelview if isinstance(modelview, list) else [modelview]
+        S = self.render_size
+        dev = torch.device("cuda", self.device)
+        ret = []
+        for t in targets:
+            color = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+            depth = torch.empty((S, S), dtype=torch.float32, device=dev)
+            mc = torch.empty((S, S), dtype=torch.float32, device=dev)
+            md = torch.empty((S, S), dtype=torch.float32, device=dev)
+            tm = _mv(t)
+            with torch.cuda.device(dev):
+                self._set_views(len(meshes))
+                _lib.check(L.ivid_warp_render(self._handle, tm.ctypes.data, 1, float(fov), _lib.ptr(color), _lib.ptr(depth),
+                                              _lib.ptr(mc), _lib.ptr(md), self._stream()))
+            self._last_raw = (color, depth, mc, md)
+            ret.append(edict({
+                "color": color.cpu().numpy(),
+                "depth": depth.cpu().numpy()[..., None],
+                "mask_color": mc.cpu().numpy()[..., None] > 0.5,
+                "mask_depth": md.cpu().numpy()[..., None] > 0.5,
+            }))
+        return ret if len(ret) > 1 else ret[0]
+
+    def _set_views(self, n):
+        cur = ctypes.c_int()
+        _lib.check(_lib.lib().ivid_warp_num_views(self._handle, ctypes.byref(cur)))
+        assert cur.value >= n, "render: meshes were not uploaded (is_autoregressive=True needs every view rendered once)"
+        if cur.value != n:
+            raise AssertionError(f"renderer holds {cur.value} views but {n} meshes were passed; create a new renderer per sample")
+
+
+class DeviceWarp(_Native):
+    """Device-resident replacement of the per-sample `[AggregationRenderer(...)]` list + mesh lists of
+    inference/sample.py:50,57-58: every sample's source views (RGBD) stay on the GPU."""
+
+    def __init__(self, batch, image_size=128, ssaa=3, max_views=27, near=0.01, far=200.0, device=None):
+        device = torch.cuda.current_device() if device is None else device
+        super().__init__(image_size, image_size * ssaa, max_views, batch, near, far, device)
+
+    def reset(self):
+        _lib.check(_lib.lib().ivid_warp_reset(self._handle))
+
+    @property
+    def num_views(self):
+        n = ctypes.c_int()
+        _lib.check(_lib.lib().ivid_warp_num_views(self._handle, ctypes.byref(n)))
+        return n.value
+
+    def _mvs(self, modelviews):
+        """-> (float32 [k,4,4] array, shared flag).  A list of `batch` matrices is per-sample, anything else is shared."""
+        if isinstance(modelviews, (list, tuple)) and len(modelviews) == self.batch:
+            try:
+                per = [_mv(m) for m in modelviews]
+                return np.ascontiguousarray(np.stack(per)), 0
+            except (AssertionError, TypeError, ValueError, IndexError):
+                pass
+        return _mv(modelviews)[None].copy(), 1
+
+    def add_view(self, rgbd, modelviews, fov=45, near=0.6, far=5, atol=0.03, rtol=0.03, erode_rgb=3):
+        """rgbd: cuda fp32 [B,4,H,W] sampler output in [-1,1]; modelviews: one 4x4 (shared) or a list of B."""
+        assert rgbd.is_cuda and rgbd.shape == (self.batch, 4, self.image_size, self.image_size)
+        r = rgbd.to(torch.float32).contiguous()
+        mv, shared = self._mvs(modelviews)
+        p = warp_params(fov, near, far, atol, rtol, erode_rgb)
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.lib().ivid_warp_add_view(self._handle, _lib.ptr(r), mv.ctypes.data, shared, ctypes.byref(p), self._stream()))
+
+    def aggregate(self, modelviews, fov=45, near=0.6, far=5, atol=0.03, rtol=0.03, erode_rgb=3):
+        """aggregate_conditions for every sample -> cuda fp32 [B,7,H,W]: color(3), depth, mask, mask_rgb, depth_convex."""
+        dev = torch.device("cuda", self.device)
+        out = torch.empty((self.batch, 7, self.image_size, self.image_size), dtype=torch.float32, device=dev)
+        mv, shared = self._mvs(modelviews)
+        p = warp_params(fov, near, far, atol, rtol, erode_rgb)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ivid_warp_aggregate(self._handle, mv.ctypes.data, shared, ctypes.byref(p), _lib.ptr(out), self._stream()))
+        return out
+
+    def render_raw(self, modelviews, fov=45):
+        dev = torch.device("cuda", self.device)
+        S, B = self.render_size, self.batch
+        color = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+        mc = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+        md = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+        mv, shared = self._mvs(modelviews)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ivid_warp_render(self._handle, mv.ctypes.data, shared, float(fov), _lib.ptr(color), _lib.ptr(depth),
+                                                   _lib.ptr(mc), _lib.ptr(md), self._stream()))
+        return color, depth, mc, md
+
+    def get_mesh(self, sample, view):
+        n = self.image_size
+        V, F = (n + 2) ** 2, 2 * (n + 1) ** 2
+        vb = np.empty((V, 9), np.float32); faces = np.empty((F, 3), np.uint32); col = np.empty((n, n, 3), np.float32)
+        _lib.check(_lib.lib().ivid_warp_get_mesh(self._handle, sample, view, vb.ctypes.data, faces.ctypes.data, col.ctypes.data))
+        return vb, faces, col
