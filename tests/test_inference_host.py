@@ -1,0 +1,95 @@
+"""CPU: host logic of the sampling driver — view sets, per-rank sharding (incl. a world_size-2 gloo run), scene format."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ivid_b200.inference import build_modelviews, load_scene, parse_int_list, reorder, save_scene, shard
+from ivid_b200.utils import edict
+
+
+def test_parse_int_list_and_reorder():
+    assert parse_int_list("0-3,7,9-10") == [0, 1, 2, 3, 7, 9, 10]
+    data = [torch.full((1,), float(i)) for i in range(27)]
+    out = reorder(data, "3x9")
+    assert out.shape == (27, 1) and out[13].item() == 0.0 and out[0].item() == 23.0     # view 0 sits in the grid centre
+    assert reorder(data[1:], "3x9")[13].item() == -1.0                                  # 26 cond views: blank first cell
+    with pytest.raises(NotImplementedError):
+        reorder(data, "bogus")
+
+
+def test_viewsets():
+    v = build_modelviews("3x9", 1)
+    assert len(v) == 27 and np.allclose(v[0], build_modelviews("uncond", 1)[0])
+    eye = np.linalg.inv(v[1].astype(np.float64))[:3, 3]
+    assert np.allclose(eye, [0, np.sin(0.15), np.cos(0.15)], atol=1e-6)                 # yaw 0, pitch +0.15 (sample.py:324-336)
+    r = build_modelviews("random", 3, rng=np.random.default_rng(0))
+    assert len(r) == 3 and len(r[0]) == 2
+    for m in v:
+        assert np.allclose(np.linalg.norm(np.linalg.inv(m.astype(np.float64))[:3, 3]), 1.0, atol=1e-6)   # eyes on the unit sphere
+    with pytest.raises(NotImplementedError):
+        build_modelviews("nope", 1)
+
+
+def test_shard_partition():
+    items = list(range(23))
+    for w in (1, 2, 4, 8):
+        parts = [shard(items, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == items and max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert shard(None, 0, 2) is None
+
+
+def test_scene_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    meshes = [edict(depth=rng.uniform(0.6, 5, (16, 16, 1)).astype(np.float32), fov=45, modelview=build_modelviews("uncond", 1)[0]) for _ in range(2)]
+    colors = [rng.uniform(0, 1, (16, 16, 3)).astype(np.float32) for _ in range(2)]
+    p = os.path.join(tmp_path, "scene.npz")
+    save_scene(p, meshes, colors)
+    back = load_scene(p)
+    for m, c, b in zip(meshes, colors, back):
+        assert np.array_equal(b.depth, m.depth)                                          # float32 bits survive the RGBA8 PNG
+        assert np.array_equal((np.clip(c * 255, 0, 255)).astype(np.uint8), np.round(b.color * 255).astype(np.uint8))
+        assert b.fov == 45
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seeds = list(range(11))
+    mine = shard(seeds, rank, world)
+    # weights: rank 0 holds the packed arena, everyone else receives it with ONE broadcast (bench.py / sample driver)
+    arena = torch.arange(1024, dtype=torch.uint8) if rank == 0 else torch.zeros(1024, dtype=torch.uint8)
+    dist.broadcast(arena, src=0)
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                                             # max-over-ranks timing reduction
+    q.put((rank, mine, bool(torch.equal(arena, torch.arange(1024, dtype=torch.uint8))), got, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, mine, ok, got, tmax in res:
+        assert ok and tmax == 2.0
+        assert sorted(got[0] + got[1]) == list(range(11)) and not set(got[0]) & set(got[1])
+        assert mine == list(range(11))[rank::2]
