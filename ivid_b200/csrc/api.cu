@@ -221,19 +221,19 @@ int ivid_op_group_norm(const float* x0_dev, int C0, const float* x1_dev, int C1,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int C = C0 + (x1_dev ? C1 : 0);
     if (!x1_dev) C1 = 0;
-    DevBuf dg(C * 4), dbt(C * 4), st0(static_cast<size_t>(N) * C0 * 16), st1(static_cast<size_t>(N) * std::max(C1, 1) * 16),
-        ab(static_cast<size_t>(N) * C * 8);
+    DevBuf dg(C * 4), dbt(C * 4), st0(static_cast<size_t>(N) * C0 * 16), st1(static_cast<size_t>(N) * std::max(C1, 1) * 16);
     IVID_CHECK_CUDA(cudaMemcpyAsync(dg.p, gamma_host, C * 4, cudaMemcpyHostToDevice, st));
     IVID_CHECK_CUDA(cudaMemcpyAsync(dbt.p, beta_host, C * 4, cudaMemcpyHostToDevice, st));
     IVID_CHECK_CUDA(cudaMemsetAsync(st0.p, 0, static_cast<size_t>(N) * C0 * 16, st));
     IVID_CHECK_CUDA(cudaMemsetAsync(st1.p, 0, static_cast<size_t>(N) * std::max(C1, 1) * 16, st));
     launch_gn_stats(x0_dev, static_cast<double*>(st0.p), N, H * W, C0, st);
     if (C1 > 0) launch_gn_stats(x1_dev, static_cast<double*>(st1.p), N, H * W, C1, st);
-    launch_gn_coeff(static_cast<double*>(st0.p), C1 > 0 ? static_cast<double*>(st1.p) : nullptr, C0, C1, N, groups, H * W,
-                    eps, static_cast<float*>(dg.p), static_cast<float*>(dbt.p), film_dev, 2 * C, 0, ab.p, st);
     GnApplyDesc g;
     g.x0 = x0_dev; g.x1 = C1 > 0 ? x1_dev : nullptr; g.C0 = C0; g.C1 = C1; g.N = N; g.H = H; g.W = W; g.mode = mode;
-    g.silu = silu; g.ab = ab.p; g.out_act = out_fp16_dev;
+    g.silu = silu; g.out_act = out_fp16_dev;
+    g.stats0 = static_cast<double*>(st0.p); g.stats1 = C1 > 0 ? static_cast<double*>(st1.p) : nullptr;
+    g.groups = groups; g.eps = eps; g.gamma = static_cast<float*>(dg.p); g.beta = static_cast<float*>(dbt.p);
+    g.film = film_dev; g.film_ld = 2 * C; g.film_off = 0;
     launch_gn_apply(g, st);
     IVID_CHECK_CUDA(cudaStreamSynchronize(st));
   });

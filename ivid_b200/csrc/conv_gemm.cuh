@@ -36,6 +36,7 @@ struct ConvGemmParams {
   const float* bias;           // [Cout_pad] fp32
   const float* residual;       // fp32 NHWC or nullptr
   void* out;
+  double* stats;               // optional [N][Cout][2] per-(sample, channel) sum / sum-of-squares of the output (GroupNorm)
 };
 
 template <int BN>
@@ -48,7 +49,8 @@ struct ConvGemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : (BN == 64) ? 8 : 10;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024 alignment slack
+  static constexpr int STAT_BYTES = 8 * BN * 4;                                // [4 warps][sum|sumsq][BN] fp32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;   // +1024 alignment slack
   static constexpr int THREADS = 256;
 };
 
@@ -66,6 +68,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(bar_area + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,6 +189,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const bool do_stats = (CH == 32) && (p.stats != nullptr);
+      const int n_warp = tn * p.TN + (quarter * 32) / (p.TW * p.TH);     // sample of this warp's 32 rows (TW*TH >= 32)
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t r[CH];
@@ -193,10 +198,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         else tmem_ld_32x32b_x16(taddr + c0, r);
         tc_wait_ld();
         const int col0 = nblk * BN + c0;
-        if (valid && col0 < p.Cout) {
-          float v[CH];
+        if (col0 >= p.Cout) continue;                   // padded output columns (warp-uniform)
+        float v[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
+        for (int j = 0; j < CH; ++j) v[j] = valid ? __uint_as_float(r[j]) + __ldg(p.bias + col0 + j) : 0.f;
+        if (valid) {
           if (p.out_mode == 2) {
             // fp32 NCHW planes (final eps output): Cout is tiny (4)
             float* o = reinterpret_cast<float*>(p.out);
@@ -237,6 +243,54 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
           }
         }
+        if constexpr (CH == 32) {
+          if (do_stats) {
+            // GroupNorm statistics of the tensor being written (consumed by the NEXT norm): per-column sum and sum of
+            // squares over this warp's 32 rows by a transposing butterfly (31 shuffles per quantity); lane l ends up
+            // with column c0 + l.
+            float q[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) q[j] = v[j] * v[j];
+#pragma unroll
+            for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < cnt / 2; ++i) {
+                const float send_v = up ? v[i] : v[i + cnt / 2];
+                const float keep_v = up ? v[i + cnt / 2] : v[i];
+                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, off);
+                const float send_q = up ? q[i] : q[i + cnt / 2];
+                const float keep_q = up ? q[i + cnt / 2] : q[i];
+                q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
+            }
+            if (p.TN == 1) {
+              stat_smem[(quarter * 2 + 0) * BN + c0 + lane] = v[0];
+              stat_smem[(quarter * 2 + 1) * BN + c0 + lane] = q[0];
+            } else if (n_warp < p.N && col0 + lane < p.Cout) {
+              double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + col0 + lane) * 2;
+              atomicAdd(st, static_cast<double>(v[0]));
+              atomicAdd(st + 1, static_cast<double>(q[0]));
+            }
+          }
+        }
+      }
+      if (do_stats && p.TN == 1) {
+        // combine the four epilogue warps (same sample when TN == 1), then one double atomic per (column, moment)
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const int t = threadIdx.x - 128;
+        for (int c = t; c < BN; c += 128) {
+          const int col = nblk * BN + c;
+          if (col < p.Cout && n_warp < p.N) {
+            float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
+            double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
+            atomicAdd(st, static_cast<double>(ssum));
+            atomicAdd(st + 1, static_cast<double>(qsum));
+          }
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();

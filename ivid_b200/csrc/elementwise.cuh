@@ -75,52 +75,13 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 }
 
 // ----------------------------------------------------------------------------------------------
-// GroupNorm coefficients.  grid = N, block = 256.  Channels c in [0, C0) come from stats0, [C0, C0+C1) from stats1.
-//   A[n][c] = rstd*gamma*(1+scale),  B[n][c] = (beta - mean*rstd*gamma)*(1+scale) + shift
-// film: [N][film_ld] table; scale = film[n][film_off + c], shift = film[n][film_off + C + c]  (torch.chunk(emb_out, 2)).
-// ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_coeff_kernel(const double* __restrict__ stats0, const double* __restrict__ stats1,
-                                                       int C0, int C1, int groups, double inv_count, float eps,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ film, int film_ld, int film_off,
-                                                       float2* __restrict__ ab) {
-  __shared__ float s_mean[64], s_rstd[64];
-  const int n = blockIdx.x;
-  const int C = C0 + C1;
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double* st = (c < C0) ? stats0 + (static_cast<size_t>(n) * C0 + c) * 2
-                                  : stats1 + (static_cast<size_t>(n) * C1 + (c - C0)) * 2;
-      s += st[0];
-      q += st[1];
-    }
-    const double cnt_inv = inv_count / cpg;
-    const double mean = s * cnt_inv;
-    double var = q * cnt_inv - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float a0 = s_rstd[g] * gamma[c];
-    const float b0 = beta[c] - s_mean[g] * a0;
-    float a = a0, b = b0;
-    if (film != nullptr) {
-      const float sc = 1.0f + film[static_cast<size_t>(n) * film_ld + film_off + c];
-      const float sh = film[static_cast<size_t>(n) * film_ld + film_off + C + c];
-      a = a0 * sc;
-      b = b0 * sc + sh;
-    }
-    ab[static_cast<size_t>(n) * C + c] = make_float2(a, b);
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
-// GroupNorm apply (+SiLU, +resample).  One thread = 8 channels of one OUTPUT pixel.
+// GroupNorm apply (+FiLM, +SiLU, +resample).  grid = (pixel chunks, N), block = 256.
+// Prologue (per block): group mean / rstd of sample n from the per-channel statistics of up to two sources (virtual
+// concat: channels [0,C0) from stats0, [C0,C0+C1) from stats1), folded with gamma/beta and the FiLM scale/shift into a
+// per-channel affine kept in shared memory:
+//   A[c] = rstd*gamma*(1+scale),  B[c] = (beta - mean*rstd*gamma)*(1+scale) + shift
+//   film: [N][film_ld] table; scale = film[n][film_off + c], shift = film[n][film_off + C + c]  (torch.chunk(emb_out, 2)).
+// Body: one work item = 8 channels of one OUTPUT pixel.
 //   mode 0: same resolution; 1: nearest 2x upsample (Ho = 2H); 2: 2x2 average pool (Ho = H/2)
 // ----------------------------------------------------------------------------------------------
 struct GnApplyParams {
@@ -129,7 +90,11 @@ struct GnApplyParams {
   int N, H, W;                          // INPUT spatial size
   int mode;                             // 0 same, 1 up, 2 down
   int silu;
-  const float2* ab;                     // [N][C] coefficients
+  const double* stats0; const double* stats1;   // [N][C0][2], [N][C1][2] (sum, sum of squares over H*W)
+  int groups; double inv_count; float eps;
+  const float* gamma; const float* beta;
+  const float* film; int film_ld, film_off;
+  int pix_per_block;
   __half* out_act;                      // fp16 [N][Ho][Wo][C]
   __half* out_raw16;                    // optional fp16 raw copy (same-resolution only) [N][H][W][C]
   float* out_raw32;                     // optional fp32 raw (resampled) [N][Ho][Wo][C]
@@ -145,29 +110,57 @@ __device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int 
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float s_ab[];        // A then B, each stored [c % 8][c / 8] so a warp's reads are conflict-free
+  __shared__ float s_mean[64], s_rstd[64];
   const int C = p.C0 + p.C1;
+  const int n = blockIdx.y;
+  const int cpg = C / p.groups;
+  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double* st = (c < p.C0) ? p.stats0 + (static_cast<size_t>(n) * p.C0 + c) * 2
+                                    : p.stats1 + (static_cast<size_t>(n) * p.C1 + (c - p.C0)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const double cnt_inv = p.inv_count / cpg;
+    const double mean = s * cnt_inv;
+    double var = q * cnt_inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a0 = s_rstd[g] * p.gamma[c];
+    const float b0 = p.beta[c] - s_mean[g] * a0;
+    float a = a0, b = b0;
+    if (p.film != nullptr) {
+      const float sc = 1.0f + p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c];
+      const float sh = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + C + c];
+      a = a0 * sc;
+      b = b0 * sc + sh;
+    }
+    s_ab[(c & 7) * (C >> 3) + (c >> 3)] = a;
+    s_ab[C + (c & 7) * (C >> 3) + (c >> 3)] = b;
+  }
+  __syncthreads();
+
   const int c8 = C >> 3;
   const int Ho = p.mode == 1 ? p.H * 2 : (p.mode == 2 ? p.H / 2 : p.H);
   const int Wo = p.mode == 1 ? p.W * 2 : (p.mode == 2 ? p.W / 2 : p.W);
-  const size_t total = static_cast<size_t>(p.N) * Ho * Wo * c8;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % c8);
-    size_t pix = idx / c8;
-    const int wo = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int ho = static_cast<int>(pix % Ho);
-    const int n = static_cast<int>(pix / Ho);
+  const int pix0 = blockIdx.x * p.pix_per_block;
+  const int npix = min(p.pix_per_block, Ho * Wo - pix0);
+  const int items = npix * c8;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int cg = it % c8;
+    const int pix = pix0 + it / c8;
+    const int wo = pix % Wo, ho = pix / Wo;
     const int c = cg * 8;
     float A[8], B[8];
-    {
-      const float4* abp = reinterpret_cast<const float4*>(p.ab + static_cast<size_t>(n) * C + c);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t = __ldg(abp + j);
-        A[2 * j] = t.x; B[2 * j] = t.y; A[2 * j + 1] = t.z; B[2 * j + 1] = t.w;
-      }
-    }
+    for (int j = 0; j < 8; ++j) { A[j] = s_ab[j * c8 + cg]; B[j] = s_ab[C + j * c8 + cg]; }
     float act[8], raw[8];
     if (p.mode == 2) {
 #pragma unroll

@@ -25,6 +25,10 @@ int conv_pad_cout(int cout) {
   if (cout >= 64) return ((cout + 63) / 64) * 64;
   return ((cout + 15) / 16) * 16;
 }
+bool conv_can_fuse_stats(int H, int W) {
+  const int TW = std::min(W, 16), TH = std::min(H, 128 / TW);
+  return TW * TH >= 32;
+}
 int conv_pick_bn(int cout_pad) {
   if (cout_pad % 256 == 0) return 256;
   if (cout_pad % 128 == 0) return 128;
@@ -65,6 +69,8 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   p.seg_chunks[1] = d.C1 / 64; p.seg_taps[1] = d.C1 > 0 ? d.taps1 : 0;
   p.Cout = d.cout; p.ldc = d.ldc; p.ldr = d.ldr; p.out_mode = d.out_mode;
   p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+  p.stats = (d.stats != nullptr && conv_can_fuse_stats(d.H, d.W) && d.out_mode == 0) ? d.stats : nullptr;
+  IVID_REQUIRE(d.stats == nullptr || p.stats != nullptr, "conv: fused statistics need >= 32 pixels per sample per warp");
   IVID_REQUIRE(d.out_mode == 2 || (d.cout % 8 == 0 && d.ldc % 8 == 0), "conv: NHWC output needs Cout % 8 == 0");
   const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0);
   l->mapA0 = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
@@ -158,26 +164,25 @@ void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaSt
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 
-void launch_gn_coeff(const double* stats0, const double* stats1, int C0, int C1, int N, int groups, int HW, float eps,
-                     const float* gamma, const float* beta, const float* film, int film_ld, int film_off, void* ab,
-                     cudaStream_t s) {
-  IVID_REQUIRE(groups <= 64 && (C0 + C1) % groups == 0, "group norm: groups must divide channels (<= 64 groups)");
-  gn_coeff_kernel<<<N, 256, 0, s>>>(stats0, stats1, C0, C1, groups, 1.0 / static_cast<double>(HW), eps, gamma, beta,
-                                    film, film_ld, film_off, reinterpret_cast<float2*>(ab));
-  IVID_CHECK_CUDA(cudaGetLastError());
-}
-
 void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   IVID_REQUIRE(d.C0 % 8 == 0 && d.C1 % 8 == 0, "gn_apply: channel counts must be multiples of 8");
+  const int C = d.C0 + d.C1;
+  IVID_REQUIRE(d.groups >= 1 && d.groups <= 64 && C % d.groups == 0, "group norm: groups must divide channels (<= 64 groups)");
+  IVID_REQUIRE(d.stats0 != nullptr && d.gamma != nullptr && d.beta != nullptr, "gn_apply: statistics / affine parameters missing");
   GnApplyParams p;
   p.x0 = d.x0; p.x1 = d.x1; p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
-  p.silu = d.silu; p.ab = reinterpret_cast<const float2*>(d.ab);
+  p.silu = d.silu;
+  p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
+  p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);
   p.out_raw32 = d.out_raw32;
   const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
   const int Wo = d.mode == 1 ? d.W * 2 : (d.mode == 2 ? d.W / 2 : d.W);
-  const size_t items = static_cast<size_t>(d.N) * Ho * Wo * ((d.C0 + d.C1) / 8);
-  gn_apply_kernel<<<ew_grid(items, 256), 256, 0, s>>>(p);
+  // ~8K work items (8 channels each) per block; at least one pixel
+  p.pix_per_block = std::max(1, std::min(Ho * Wo, 8192 / (C / 8)));
+  dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
+  const size_t smem = static_cast<size_t>(C) * 8;
+  gn_apply_kernel<<<grid, 256, smem, s>>>(p);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 

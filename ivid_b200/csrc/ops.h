@@ -22,6 +22,7 @@ struct ConvDesc {
   const float* bias = nullptr;                             // [cout_pad]
   const float* residual = nullptr; int ldr = 0;            // fp32 NHWC
   void* out = nullptr; int ldc = 0; int out_mode = 0;      // 0 fp32 NHWC, 1 fp16 NHWC, 2 fp32 NCHW
+  double* stats = nullptr;                                 // optional fused GroupNorm statistics of the output [N][cout][2]
   int N = 0, H = 0, W = 0;
 };
 
@@ -31,6 +32,7 @@ void conv_launch_destroy(ConvLaunch* l);
 void conv_launch_run(const ConvLaunch* l, cudaStream_t s);
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s);   // same launch, output pointer overridden
 int conv_pick_bn(int cout_pad);
+bool conv_can_fuse_stats(int H, int W);                    // epilogue statistics need >= 32 pixels of one sample per warp
 int conv_pad_cout(int cout);
 
 AttnLaunch* attn_launch_create(const void* qkv, int N, int T, int C, void* out);
@@ -38,13 +40,13 @@ void attn_launch_destroy(AttnLaunch* l);
 void attn_launch_run(const AttnLaunch* l, cudaStream_t s);
 
 void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaStream_t s);
-void launch_gn_coeff(const double* stats0, const double* stats1, int C0, int C1, int N, int groups, int HW, float eps,
-                     const float* gamma, const float* beta, const float* film, int film_ld, int film_off, void* ab,
-                     cudaStream_t s);
 struct GnApplyDesc {
   const float* x0 = nullptr; const float* x1 = nullptr; int C0 = 0, C1 = 0;
   int N = 0, H = 0, W = 0; int mode = 0; int silu = 1;
-  const void* ab = nullptr;
+  const double* stats0 = nullptr; const double* stats1 = nullptr;   // per-(sample, channel) sum / sumsq of each source
+  int groups = 32; float eps = 1e-5f;
+  const float* gamma = nullptr; const float* beta = nullptr;        // [C0 + C1]
+  const float* film = nullptr; int film_ld = 0, film_off = 0;       // optional FiLM table (scale | shift)
   void* out_act = nullptr; void* out_raw16 = nullptr; float* out_raw32 = nullptr;
 };
 void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s);

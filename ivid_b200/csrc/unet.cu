@@ -485,7 +485,13 @@ Plan* Unet::build_plan(int N) {
     float* s_emb = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
     float* s_film = static_cast<float*>(bump.take(static_cast<size_t>(N) * film_total_ * 4));
 
-    auto add_conv = [&](const ConvDesc& d) {
+    Act pending_stats; bool has_pending_stats = false;
+    auto add_conv = [&](ConvDesc d, const Act* stats_of = nullptr) {
+      // GroupNorm statistics of the output are accumulated in the conv epilogue whenever the tile geometry allows
+      const bool fused = stats_of != nullptr && conv_can_fuse_stats(d.H, d.W);
+      if (fused) d.stats = stats_of->stats;
+      if (stats_of != nullptr && !fused) pending_stats = *stats_of;
+      has_pending_stats = stats_of != nullptr && !fused;
       if (!create) return;
       ConvLaunch* l = conv_launch_create(d);
       pl->convs.push_back(l);
@@ -498,27 +504,28 @@ Plan* Unet::build_plan(int N) {
       pl->ops.push_back([l](cudaStream_t s) { conv_launch_run(l, s); });
     };
     auto add_stats = [&](const Act& a) {
-      if (!create) return;
+      if (!create || !has_pending_stats) return;      // already fused into the producing conv
+      has_pending_stats = false;
       const float* x = a.data; double* st = stats_ptr(a);
       const int HW = a.H * a.W, C = a.C;
       pl->ops.tag("gn_stats", 0, static_cast<double>(N) * HW * C * 4);
       pl->ops.push_back([=](cudaStream_t s) { launch_gn_stats(x, st, N, HW, C, s); });
     };
+    // GroupNorm coefficients are computed in the prologue of the apply kernel: add_coeff only records its inputs
+    GnApplyDesc pend;
     auto add_coeff = [&](const Act& a0, const Act* a1, const GnW& g, int film_off) {
-      if (!create) return;
-      const double* st0 = stats_ptr(a0);
-      const double* st1 = a1 ? stats_ptr(*a1) : nullptr;
-      const int C0 = a0.C, C1 = a1 ? a1->C : 0, HW = a0.H * a0.W;
-      const float* gamma = Wf(g.g_off); const float* beta = Wf(g.b_off);
-      const float* film = film_off >= 0 ? s_film : nullptr;
-      const int fl = film_total_, fo = std::max(film_off, 0);
-      pl->ops.tag("gn_coeff", 0, static_cast<double>(N) * (C0 + C1) * 24);
-      pl->ops.push_back([=](cudaStream_t s) {
-        launch_gn_coeff(st0, st1, C0, C1, N, G, HW, eps, gamma, beta, film, fl, fo, s_ab, s);
-      });
+      pend = GnApplyDesc();
+      pend.stats0 = stats_ptr(a0);
+      pend.stats1 = a1 ? stats_ptr(*a1) : nullptr;
+      pend.groups = G; pend.eps = eps;
+      pend.gamma = Wf(g.g_off); pend.beta = Wf(g.b_off);
+      pend.film = film_off >= 0 ? s_film : nullptr;
+      pend.film_ld = film_total_; pend.film_off = std::max(film_off, 0);
     };
-    auto add_apply = [&](const GnApplyDesc& d) {
+    auto add_apply = [&](GnApplyDesc d) {
       if (!create) return;
+      d.stats0 = pend.stats0; d.stats1 = pend.stats1; d.groups = pend.groups; d.eps = pend.eps; d.gamma = pend.gamma;
+      d.beta = pend.beta; d.film = pend.film; d.film_ld = pend.film_ld; d.film_off = pend.film_off;
       {
         const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
         const double in_el = static_cast<double>(d.N) * d.H * d.W * (d.C0 + d.C1);
@@ -567,7 +574,7 @@ Plan* Unet::build_plan(int N) {
       d.act0 = s_in; d.C0 = 64; d.taps0 = 9;
       d.weight = W8(in_conv_.w_off); d.cout_pad = in_conv_.cout_pad; d.cout = in_conv_.cout; d.bias = Wf(in_conv_.b_off);
       d.out = cur.data; d.ldc = cur.C; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
-      add_conv(d);
+      add_conv(d, &cur);
       add_stats(cur);
     }
     std::vector<Act> skips;
@@ -585,7 +592,7 @@ Plan* Unet::build_plan(int N) {
       add_coeff(x0, x1, r.gn1, -1);
       GnApplyDesc g1;
       g1.x0 = x0.data; g1.x1 = x1 ? x1->data : nullptr; g1.C0 = x0.C; g1.C1 = x1 ? x1->C : 0;
-      g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1; g1.ab = s_ab;
+      g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1;
       g1.out_act = s_a1; g1.out_raw16 = r.skip_conv ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
       IVID_REQUIRE(!(r.skip_conv && r.mode != 0), "internal: up/down ResBlocks keep the channel count");
       add_apply(g1);
@@ -597,13 +604,13 @@ Plan* Unet::build_plan(int N) {
         d.act0 = s_a1; d.C0 = r.cin; d.taps0 = 9;
         d.weight = W8(r.conv1.w_off); d.cout_pad = r.conv1.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv1.b_off);
         d.out = h.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
-        add_conv(d);
+        add_conv(d, &h);
         add_stats(h);
       }
       // GN2 * (1+scale) + shift, SiLU -> a2
       add_coeff(h, nullptr, r.gn2, r.film_off);
       GnApplyDesc g2;
-      g2.x0 = h.data; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1; g2.ab = s_ab;
+      g2.x0 = h.data; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1;
       g2.out_act = s_a2;
       add_apply(g2);
       // conv2 (+ 1x1 skip as extra K) + residual -> out
@@ -615,7 +622,7 @@ Plan* Unet::build_plan(int N) {
         d.weight = W8(r.conv2.w_off); d.cout_pad = r.conv2.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv2.b_off);
         if (identity) { d.residual = need_xr ? s_xr : x0.data; d.ldr = r.cout; }
         d.out = out.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
-        add_conv(d);
+        add_conv(d, &out);
         add_stats(out);
       }
       return out;
@@ -625,7 +632,7 @@ Plan* Unet::build_plan(int N) {
       const int T = x.H * x.W;
       add_coeff(x, nullptr, a.gn, -1);
       GnApplyDesc g;
-      g.x0 = x.data; g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.ab = s_ab; g.out_act = s_a1;
+      g.x0 = x.data; g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.out_act = s_a1;
       add_apply(g);
       {
         ConvDesc d;
@@ -647,7 +654,7 @@ Plan* Unet::build_plan(int N) {
         d.weight = W8(a.proj.w_off); d.cout_pad = a.proj.cout_pad; d.cout = a.C; d.bias = Wf(a.proj.b_off);
         d.residual = x.data; d.ldr = a.C;
         d.out = out.data; d.ldc = a.C; d.out_mode = 0; d.N = N; d.H = x.H; d.W = x.W;
-        add_conv(d);
+        add_conv(d, &out);
         add_stats(out);
       }
       return out;
@@ -677,7 +684,7 @@ Plan* Unet::build_plan(int N) {
     // ---- output head: GN + SiLU + conv3x3 -> eps (fp32 NCHW) ----
     add_coeff(cur, nullptr, out_gn_, -1);
     GnApplyDesc go;
-    go.x0 = cur.data; go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.ab = s_ab; go.out_act = s_a1;
+    go.x0 = cur.data; go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.out_act = s_a1;
     add_apply(go);
     if (create) {
       ConvDesc d;
