@@ -299,9 +299,13 @@ def main():
     L = _lib.lib()
     _lib.check(L.ivid_unet_profile_begin(net._handle))
     dstep(x, 1)
-    buf = ctypes.create_string_buffer(1 << 16)
+    buf = ctypes.create_string_buffer(1 << 19)
     _lib.check(L.ivid_unet_profile_end(net._handle, buf, len(buf)))
     prof = json.loads(buf.value.decode())
+    per_op = prof.pop("_ops", None)
+    if per_op is not None and rank == 0:
+        with open(os.path.join(ROOT, "gpurun_out", "per_op_profile.json"), "w") as f:
+            json.dump(per_op, f)
     peaks = _peaks()
     dom = max((k for k in prof if k.startswith("conv_gemm")), key=lambda k: prof[k]["ms"])
     d = prof[dom]

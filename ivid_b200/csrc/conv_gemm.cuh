@@ -37,6 +37,8 @@ struct ConvGemmParams {
   const float* residual;       // fp32 NHWC or nullptr
   void* out;
   double* stats;               // optional [N][Cout][2] per-(sample, channel) sum / sum-of-squares of the output (GroupNorm)
+  int epi_tma;                 // fp32 NHWC output (and residual) moved by TMA through swizzled shared-memory tiles
+  int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
 
 template <int BN>
@@ -46,28 +48,33 @@ struct ConvGemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : (BN == 64) ? 8 : 10;
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128) ? 4 : (BN == 64) ? 5 : 6;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAT_BYTES = 8 * BN * 4;                                // [4 warps][sum|sumsq][BN] fp32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;   // +1024 alignment slack
+  // per epilogue warp: 2 output staging tiles + 2 residual tiles of [32 pixels][32 channels] fp32 (4 KB each, 128B-swizzled)
+  static constexpr int EPI_BYTES = 4 * 4 * 32 * 32 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
   static constexpr int THREADS = 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                 const __grid_constant__ CUtensorMap mapRes, const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_area = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;            // 1024-aligned (TMA 128B swizzle)
+  uint8_t* bar_area = stage_smem + Cfg::EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;                               // [4 warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
   float* stat_smem = reinterpret_cast<float*>(bar_area + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -87,6 +94,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
@@ -175,6 +183,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = (BN >= 32) ? 32 : 16;
+    // ---- TMA epilogue state (CH == 32, fp32 NHWC): the warp's 32 rows form one box (32 ch, TW, box_h, box_n)
+    constexpr int NCH = BN / 32;
+    uint8_t* epi_base = stage_smem + quarter * 16384;               // out0 | out1 | res0 | res1, 4 KB each
+    uint64_t* res_bar = res_full + quarter * 2;
+    const int box_h0 = (p.TW * p.TH >= 32) ? ((quarter * 32) / p.TW) % p.TH : 0;
+    const int box_n0 = (quarter * 32) / (p.TW * p.TH);
+    const bool tma_res = p.epi_tma && p.residual != nullptr && !(p.debug & 2);
+    uint32_t res_cnt = 0, res_issued = 0, out_cnt = 0;
+    const uint32_t my_tiles = (static_cast<int>(blockIdx.x) < p.num_tiles)
+                                  ? static_cast<uint32_t>((p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) : 0u;
+    const uint32_t total_seq = my_tiles * NCH;
+    auto issue_res = [&](uint32_t seq) {      // lane 0: residual tile of chunk `seq` of this CTA's chunk stream
+      const int t2 = static_cast<int>(blockIdx.x) + static_cast<int>(seq / NCH) * static_cast<int>(gridDim.x);
+      const int k2 = static_cast<int>(seq % NCH);
+      const int nblk2 = t2 % p.n_blocks, mt2 = t2 / p.n_blocks;
+      const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
+      const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
+      uint64_t* bar = &res_bar[seq & 1];
+      mbar_arrive_expect_tx(bar, 4096);
+      tma_load_4d(&mapRes, bar, epi_base + 8192 + (seq & 1) * 4096, nblk2 * BN + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
+                  tn2 * p.TN + box_n0);
+    };
+    if constexpr (CH == 32) {
+      if (tma_res) {
+        if (lane == 0) { if (total_seq > 0) issue_res(0); if (total_seq > 1) issue_res(1); }
+        res_issued = total_seq < 2 ? total_seq : 2;
+      }
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nblk = tile % p.n_blocks;
       const int mt = tile / p.n_blocks;
@@ -186,117 +222,236 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       const bool do_stats = (CH == 32) && (p.stats != nullptr);
       const int n_warp = tn * p.TN + (quarter * 32) / (p.TW * p.TH);     // sample of this warp's 32 rows (TW*TH >= 32)
+      if constexpr (CH == 16) {
+        // narrow output head (Cout <= 16, fp32 NCHW eps planes or tiny NHWC): direct stores, one row per thread
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr + c0, r);
-        else tmem_ld_32x32b_x16(taddr + c0, r);
-        tc_wait_ld();
-        const int col0 = nblk * BN + c0;
-        if (col0 >= p.Cout) continue;                   // padded output columns (warp-uniform)
-        float v[CH];
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          tmem_ld_32x32b_x16(taddr + c0, r);
+          tc_wait_ld();
+          const int col0 = nblk * BN + c0;
+          if (!valid || col0 >= p.Cout) continue;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = valid ? __uint_as_float(r[j]) + __ldg(p.bias + col0 + j) : 0.f;
-        if (valid) {
-          if (p.out_mode == 2) {
-            // fp32 NCHW planes (final eps output): Cout is tiny (4)
-            float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const int c = col0 + j;
-              if (c < p.Cout) o[((static_cast<size_t>(n) * p.Cout + c) * p.H + h) * p.W + w] = v[j];
-            }
-          } else {
-            if (p.residual != nullptr) {
-              const float* rp = p.residual + pix * p.ldr + col0;
-#pragma unroll
-              for (int j = 0; j < CH; j += 4) {
-                if (col0 + j < p.Cout) {
-                  const float4 t = ldg_f4(rp + j);
-                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-              }
-            }
-            if (p.out_mode == 0) {
-              float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + col0;
-#pragma unroll
-              for (int j = 0; j < CH; j += 4)
-                if (col0 + j < p.Cout) stg_f4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          for (int j = 0; j < CH; ++j) {
+            const int c = col0 + j;
+            if (c >= p.Cout) continue;
+            float v = __uint_as_float(r[j]) + __ldg(p.bias + c);
+            if (p.out_mode == 2) {
+              reinterpret_cast<float*>(p.out)[((static_cast<size_t>(n) * p.Cout + c) * p.H + h) * p.W + w] = v;
             } else {
-              __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldc + col0;
-#pragma unroll
-              for (int j = 0; j < CH; j += 8) {
-                if (col0 + j < p.Cout) {
-                  uint4 pk;
-                  pk.x = pack_h2(v[j], v[j + 1]);
-                  pk.y = pack_h2(v[j + 2], v[j + 3]);
-                  pk.z = pack_h2(v[j + 4], v[j + 5]);
-                  pk.w = pack_h2(v[j + 6], v[j + 7]);
-                  *reinterpret_cast<uint4*>(o + j) = pk;
-                }
-              }
+              if (p.residual != nullptr) v += __ldg(p.residual + pix * p.ldr + c);
+              if (p.out_mode == 0) reinterpret_cast<float*>(p.out)[pix * p.ldc + c] = v;
+              else reinterpret_cast<__half*>(p.out)[pix * p.ldc + c] = __float2half_rn(v);
             }
           }
         }
-        if constexpr (CH == 32) {
+      } else if (p.epi_tma) {
+        // TMA epilogue (fp32 NHWC): per 32-column chunk the warp adds bias (+ residual tile fetched by TMA two chunks
+        // ahead, across tile boundaries) in the row-per-lane layout, writes the 128B-swizzled [32 px][32 ch] tile to
+        // shared memory and one lane issues a bulk tensor store; posted LSU stores from a single warp per SM
+        // sub-partition cannot keep enough bytes in flight, the TMA engine can.
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int k = 0; k < NCH; ++k) {
+          const int c0 = k * 32;
+          const int col0 = nblk * BN + c0;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          float4 b4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = ldg_f4(p.bias + col0 + 4 * j);
+          if (tma_res) mbar_wait(&res_bar[res_cnt & 1], (res_cnt >> 1) & 1);
+          tc_wait_ld();
+          if (lane == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has finished reading its tile
+          __syncwarp();
+          float4* ob = reinterpret_cast<float4*>(epi_base + (out_cnt & 1) * 4096);
+          const float4* rb = reinterpret_cast<const float4*>(epi_base + 8192 + (res_cnt & 1) * 4096);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int pos = lane * 8 + (j ^ (lane & 7));
+            float4 v = make_float4(__uint_as_float(r[4 * j]) + b4[j].x, __uint_as_float(r[4 * j + 1]) + b4[j].y,
+                                   __uint_as_float(r[4 * j + 2]) + b4[j].z, __uint_as_float(r[4 * j + 3]) + b4[j].w);
+            if (tma_res) { const float4 t = rb[pos]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+            if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the batch tail: clipped by TMA, zero for the statistics
+            ob[pos] = v;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (!(p.debug & 2)) tma_store_4d(&mapOut, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
+            tma_store_commit();
+            if (tma_res && res_issued < total_seq) issue_res(res_issued);
+          }
+          if (tma_res) { if (res_issued < total_seq) ++res_issued; ++res_cnt; }
+          ++out_cnt;
           if (do_stats) {
-            // GroupNorm statistics of the tensor being written (consumed by the NEXT norm): per-column sum and sum of
-            // squares over this warp's 32 rows by a transposing butterfly (31 shuffles per quantity); lane l ends up
-            // with column c0 + l.
-            float q[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) q[j] = v[j] * v[j];
-#pragma unroll
-            for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < cnt / 2; ++i) {
-                const float send_v = up ? v[i] : v[i + cnt / 2];
-                const float keep_v = up ? v[i + cnt / 2] : v[i];
-                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, off);
-                const float send_q = up ? q[i] : q[i + cnt / 2];
-                const float keep_q = up ? q[i + cnt / 2] : q[i];
-                q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-              }
-            }
-            if (p.TN == 1) {
-              stat_smem[(quarter * 2 + 0) * BN + c0 + lane] = v[0];
-              stat_smem[(quarter * 2 + 1) * BN + c0 + lane] = q[0];
-            } else if (n_warp < p.N && col0 + lane < p.Cout) {
-              double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + col0 + lane) * 2;
-              atomicAdd(st, static_cast<double>(v[0]));
-              atomicAdd(st + 1, static_cast<double>(q[0]));
-            }
-          }
-        }
-      }
-      if (do_stats && p.TN == 1) {
-        // combine the four epilogue warps (same sample when TN == 1), then one double atomic per (column, moment)
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        const int t = threadIdx.x - 128;
-        for (int c = t; c < BN; c += 128) {
-          const int col = nblk * BN + c;
-          if (col < p.Cout && n_warp < p.N) {
+            // column sums over the warp's 32 rows straight from the staged tile: lane = column
+            const float* of = reinterpret_cast<const float*>(ob);
             float ssum = 0.f, qsum = 0.f;
 #pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
-            double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
-            atomicAdd(st, static_cast<double>(ssum));
-            atomicAdd(st + 1, static_cast<double>(qsum));
+            for (int rr = 0; rr < 32; ++rr) {
+              const float x = of[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+              ssum += x;
+              qsum = fmaf(x, x, qsum);
+            }
+            if (p.TN == 1) {
+              stat_smem[(quarter * 2 + 0) * BN + c0 + lane] = ssum;
+              stat_smem[(quarter * 2 + 1) * BN + c0 + lane] = qsum;
+            } else if (n_warp < p.N) {
+              double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + col0 + lane) * 2;
+              atomicAdd(st, static_cast<double>(ssum));
+              atomicAdd(st + 1, static_cast<double>(qsum));
+            }
           }
         }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (do_stats && p.TN == 1) {
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          const int t = threadIdx.x - 128;
+          for (int c = t; c < BN; c += 128) {
+            const int col = nblk * BN + c;
+            if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
+              float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
+              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
+              atomicAdd(st, static_cast<double>(ssum));
+              atomicAdd(st + 1, static_cast<double>(qsum));
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+      } else {
+        // Coalesced epilogue: the warp's 32 rows x 32 columns chunk goes TMEM -> registers (row per lane) -> XOR-swizzled
+        // shared memory -> registers (8 lanes per row, 4 columns each), so every global access is a full 128-byte row
+        // segment.  Bias, residual, GroupNorm statistics and the output cast are applied in that second layout.
+        float4* stage = reinterpret_cast<float4*>(stage_smem) + quarter * 256;      // [32 rows][8 float4], 4 KB per warp
+        const int sub_row = lane >> 3, cq = lane & 7;
+        // pixel offsets / validity of the 8 rows this lane touches in the second layout
+        size_t pix_i[8];
+        bool ok_i[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int R = quarter * 32 + i * 4 + sub_row;
+          const int rw = R % p.TW, rh = (R / p.TW) % p.TH, rn = R / (p.TW * p.TH);
+          const int nn = tn * p.TN + rn, hh = th * p.TH + rh, ww = tw * p.TW + rw;
+          ok_i[i] = (nn < p.N) && (hh < p.H) && (ww < p.W);
+          pix_i[i] = (static_cast<size_t>(nn) * p.H + hh) * p.W + ww;
+        }
+        // residual / bias of the first chunk are requested before the accumulator is even ready; inside the loop the
+        // NEXT chunk's are requested before the current chunk is processed, so one warp keeps 2 x 4 KB of reads in flight
+        // (the single epilogue warp per SM sub-partition is otherwise bound by global-load latency, not bandwidth).
+        const bool has_res = p.residual != nullptr && !(p.debug & 2);
+        float4 res_nx[8], b4_nx;
+        auto prefetch = [&](int c0n) {
+          const int colq_n = nblk * BN + c0n + cq * 4;
+          const bool okc = colq_n < p.Cout;
+          b4_nx = okc ? ldg_f4(p.bias + colq_n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            res_nx[i] = (has_res && okc && ok_i[i]) ? ldg_f4(p.residual + pix_i[i] * p.ldr + colq_n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        prefetch(0);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tc_wait_ld();
+          const int col0 = nblk * BN + c0;
+          if (col0 >= p.Cout) continue;                   // padded output columns (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            stage[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+          const int colq = col0 + cq * 4;
+          const bool col_ok = colq < p.Cout;
+          float4 res[8];
+          const float4 b4 = b4_nx;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res[i] = res_nx[i];
+          if (c0 + CH < BN) prefetch(c0 + CH);
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + sub_row;
+            float4 v = stage[rr * 8 + (cq ^ (rr & 7))];
+            if (ok_i[i] && col_ok && !(p.debug & 2)) {
+              v.x = (v.x + b4.x) + res[i].x; v.y = (v.y + b4.y) + res[i].y; v.z = (v.z + b4.z) + res[i].z; v.w = (v.w + b4.w) + res[i].w;
+              if (p.out_mode == 0) {
+                stg_f4(reinterpret_cast<float*>(p.out) + pix_i[i] * p.ldc + colq, v);
+              } else {
+                uint2 pk;
+                pk.x = pack_h2(v.x, v.y);
+                pk.y = pack_h2(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix_i[i] * p.ldc + colq) = pk;
+              }
+              s4[0] += v.x; s4[1] += v.y; s4[2] += v.z; s4[3] += v.w;
+              q4[0] += v.x * v.x; q4[1] += v.y * v.y; q4[2] += v.z * v.z; q4[3] += v.w * v.w;
+            }
+          }
+          __syncwarp();
+          if (do_stats) {
+            // GroupNorm statistics of the tensor being written (consumed by the NEXT norm): reduce the 4 lanes that
+            // share a column quad; lanes 0..7 then own columns [col0 + 4*lane, +4)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], 8);
+              q4[k] += __shfl_xor_sync(0xffffffffu, q4[k], 8);
+              s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], 16);
+              q4[k] += __shfl_xor_sync(0xffffffffu, q4[k], 16);
+            }
+            if (lane < 8) {
+              if (p.TN == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  stat_smem[(quarter * 2 + 0) * BN + c0 + lane * 4 + k] = s4[k];
+                  stat_smem[(quarter * 2 + 1) * BN + c0 + lane * 4 + k] = q4[k];
+                }
+              } else if (n_warp < p.N && col_ok) {
+                double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + colq) * 2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  atomicAdd(st + 2 * k, static_cast<double>(s4[k]));
+                  atomicAdd(st + 2 * k + 1, static_cast<double>(q4[k]));
+                }
+              }
+            }
+          }
+        }
+        if (do_stats && p.TN == 1) {
+          // combine the four epilogue warps (same sample when TN == 1), then one double atomic per (column, moment)
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          const int t = threadIdx.x - 128;
+          for (int c = t; c < BN; c += 128) {
+            const int col = nblk * BN + c;
+            if (col < p.Cout && n_warp < p.N) {
+              float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
+              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
+              if (!(p.debug & 1)) {
+                atomicAdd(st, static_cast<double>(ssum));
+                atomicAdd(st + 1, static_cast<double>(qsum));
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.epi_tma && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

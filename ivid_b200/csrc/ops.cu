@@ -2,6 +2,7 @@
 #include "ops.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "attention.cuh"
@@ -15,7 +16,7 @@ namespace ivid {
 // conv implicit GEMM
 // --------------------------------------------------------------------------------------------------
 struct ConvLaunch {
-  CUtensorMap mapA0, mapA1, mapB;
+  CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;
   ConvGemmParams p;
   int BN;
   int grid;
@@ -69,6 +70,11 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   p.seg_chunks[1] = d.C1 / 64; p.seg_taps[1] = d.C1 > 0 ? d.taps1 : 0;
   p.Cout = d.cout; p.ldc = d.ldc; p.ldr = d.ldr; p.out_mode = d.out_mode;
   p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+  {
+    const char* dbg = getenv("IVID_CONV_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    if (p.debug & 8) { /* 8 = no fused statistics at all */ }
+  }
   p.stats = (d.stats != nullptr && conv_can_fuse_stats(d.H, d.W) && d.out_mode == 0) ? d.stats : nullptr;
   IVID_REQUIRE(d.stats == nullptr || p.stats != nullptr, "conv: fused statistics need >= 32 pixels per sample per warp");
   IVID_REQUIRE(d.out_mode == 2 || (d.cout % 8 == 0 && d.ldc % 8 == 0), "conv: NHWC output needs Cout % 8 == 0");
@@ -76,6 +82,21 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   l->mapA0 = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
   l->mapA1 = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : l->mapA0;
   l->mapB = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN);
+  // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
+  l->mapOut = l->mapA0; l->mapRes = l->mapA0;
+  p.epi_tma = 0;
+  if (d.out_mode == 0 && l->BN >= 32 && d.cout % 32 == 0 && !(p.debug & 16)) {
+    const int bh = std::min(p.TH, 32 / p.TW), bn = 32 / (p.TW * bh);
+    auto f32_map = [&](const void* base, int ld) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.N)};
+      const uint64_t str[3] = {static_cast<uint64_t>(ld) * 4, static_cast<uint64_t>(d.W) * ld * 4, static_cast<uint64_t>(d.H) * d.W * ld * 4};
+      const uint32_t box[4] = {32, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+      return make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    l->mapOut = f32_map(d.out, d.ldc);
+    if (d.residual != nullptr) l->mapRes = f32_map(d.residual, d.ldr);
+    p.epi_tma = 1;
+  }
   l->grid = std::min(p.num_tiles, sm_count());
   return l;
 }
@@ -84,8 +105,8 @@ void conv_launch_destroy(ConvLaunch* l) { delete l; }
 template <int BN>
 static void run_conv(const ConvLaunch* l, cudaStream_t s) {
   set_conv_attr<BN>();
-  conv_gemm_kernel<BN><<<l->grid, ConvGemmCfg<BN>::THREADS, ConvGemmCfg<BN>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1,
-                                                                                                l->mapB, l->p);
+  conv_gemm_kernel<BN><<<l->grid, ConvGemmCfg<BN>::THREADS, ConvGemmCfg<BN>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1, l->mapB,
+                                                                                                l->mapOut, l->mapRes, l->p);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {

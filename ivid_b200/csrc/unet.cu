@@ -353,14 +353,15 @@ struct Plan {
     const char* label;      // kernel family (profile aggregation key)
     double flops;           // algorithmic FLOPs of this launch (tensor-core ops)
     double bytes;           // algorithmic HBM bytes of this launch (memory-bound ops)
+    std::string note;       // shape description (per-op profile dump)
   };
   struct OpList {
     std::vector<OpRec> v;
-    const char* label = "other"; double flops = 0, bytes = 0;     // metadata of the next push
-    void tag(const char* l, double f, double b) { label = l; flops = f; bytes = b; }
+    const char* label = "other"; double flops = 0, bytes = 0; std::string note;    // metadata of the next push
+    void tag(const char* l, double f, double b, std::string n = "") { label = l; flops = f; bytes = b; note = std::move(n); }
     void push_back(std::function<void(cudaStream_t)> fn) {
-      v.push_back(OpRec{std::move(fn), label, flops, bytes});
-      label = "other"; flops = 0; bytes = 0;
+      v.push_back(OpRec{std::move(fn), label, flops, bytes, note});
+      label = "other"; flops = 0; bytes = 0; note.clear();
     }
   } ops;
   std::vector<ConvLaunch*> convs;
@@ -500,7 +501,10 @@ Plan* Unet::build_plan(int N) {
       static const char* names[] = {"conv_gemm<16>", "conv_gemm<64>", "conv_gemm<128>", "conv_gemm<256>"};
       const int bn = conv_pick_bn(d.cout_pad);
       pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * d.cout,
-                  M * K / (d.taps0 == 9 ? 9.0 : 1.0) * 2 + M * d.cout * (d.out_mode == 1 ? 2 : 4) + K * d.cout_pad * 2);
+                  M * K / (d.taps0 == 9 ? 9.0 : 1.0) * 2 + M * d.cout * (d.out_mode == 1 ? 2 : 4) + K * d.cout_pad * 2,
+                  std::to_string(d.H) + "x" + std::to_string(d.W) + " " + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") +
+                      "->" + std::to_string(d.cout) + " k" + std::to_string(d.taps0) + (d.residual ? " res" : "") + (d.stats ? " stats" : "") +
+                      (d.out_mode == 1 ? " f16" : ""));
       pl->ops.push_back([l](cudaStream_t s) { conv_launch_run(l, s); });
     };
     auto add_stats = [&](const Act& a) {
@@ -744,11 +748,17 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
     IVID_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     auto& agg = profile_acc_[pl->ops.v[i].label];
     agg.launches += 1; agg.ms += ms; agg.flops += pl->ops.v[i].flops; agg.bytes += pl->ops.v[i].bytes;
+    if (!pl->ops.v[i].note.empty()) {
+      char buf[256];
+      snprintf(buf, sizeof(buf), "[\"%s\", \"%s\", %.5f, %.4e]", pl->ops.v[i].label, pl->ops.v[i].note.c_str(), ms, pl->ops.v[i].flops);
+      if (!profile_ops_.empty()) profile_ops_ += ", ";
+      profile_ops_ += buf;
+    }
   }
   for (auto& e : ev) cudaEventDestroy(e);
 }
 
-void Unet::profile_begin() { profile_ = true; profile_acc_.clear(); }
+void Unet::profile_begin() { profile_ = true; profile_acc_.clear(); profile_ops_.clear(); }
 std::string Unet::profile_end() {
   profile_ = false;
   std::string js = "{";
@@ -761,6 +771,7 @@ std::string Unet::profile_end() {
              kv.second.launches, kv.second.ms, kv.second.flops, kv.second.bytes);
     js += buf;
   }
+  if (getenv("IVID_PROFILE_OPS") != nullptr) js += ", \"_ops\": [" + profile_ops_ + "]";
   js += "}";
   return js;
 }

@@ -114,6 +114,7 @@ class Unet {
   struct ProfAgg { int launches = 0; double ms = 0, flops = 0, bytes = 0; };
   bool profile_ = false;
   std::map<std::string, ProfAgg> profile_acc_;
+  std::string profile_ops_;
   std::vector<std::unique_ptr<Plan>> plans_;
   friend struct Plan;
 };
