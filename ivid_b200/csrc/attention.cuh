@@ -5,11 +5,14 @@
 // Input : qkv  fp16 [N][T][3C]  (NHWC output of the qkv 1x1 GEMM); head h owns channels [192h, 192h+192) = q|k|v.
 // Output: o    fp16 [N][T][C]   channel = 64*h + d   (== reshape(bs, -1, length) of the reference).
 //
-// One CTA per (sample, head, 128-query tile).  warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps2-5 = softmax / output (one thread per query row).  S = Q K^T accumulates in TMEM (fp32), the un-normalised
-// probabilities P are written back to TMEM as packed fp16 and consumed as the A operand of the P V product
-// (tcgen05.mma with A in TMEM, V in shared memory as an MN-major operand); the running output is rescaled in registers
-// (online softmax).  (q*s)(k*s) with s = 64^-1/4 is evaluated as (q.k) * 0.125 — an exact power of two.
+// One CTA per (sample, head, 128-query tile), 64 keys per step.  warp0 = TMA producer, warp1 = MMA issuer (+TMEM
+// alloc), warps2-5 = softmax / correction / output (one thread per query row).  Everything that is matrix-shaped lives
+// in TMEM (128 columns per CTA, so FOUR CTAs are resident per SM and hide each other's serial
+// S -> softmax -> PV chain; with head dim 64 the kernel is bound by the exp2 (MUFU) rate, not by the tensor pipe):
+//   S = Q K^T  fp32 in columns [0,64);  the un-normalised probabilities P overwrite the same columns as packed fp16 and
+//   are consumed directly as the A operand of P V (tcgen05.mma with A in TMEM, V in shared memory as an MN-major
+//   operand);  O accumulates in columns [64,128) across key blocks and is rescaled in place when the running maximum
+//   moves (online softmax).  (q*s)(k*s) with s = 64^-1/4 is evaluated as (q.k) * 0.125 — an exact power of two.
 #pragma once
 #include "common.cuh"
 
@@ -21,22 +24,22 @@ struct AttnParams {
   __half* out;        // [N][T][C]
 };
 
-template <int KV>
 struct AttnCfg {
+  static constexpr int KV = 64;
   static constexpr int Q_BYTES = 128 * 64 * 2;
   static constexpr int KV_BYTES = KV * 64 * 2;
   static constexpr int STAGES = 2;
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
-  static constexpr int TMEM_COLS = 256;     // S [0,KV) | P [128,128+KV/2) | O [192,256)
-  static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
+  static constexpr int TMEM_COLS = 128;     // S|P [0,64) , O [64,128)
+  static constexpr int COL_S = 0, COL_P = 0, COL_O = 64;
   static constexpr int THREADS = 192;
 };
 
-template <int KV>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 4)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                  const AttnParams p) {
-  using Cfg = AttnCfg<KV>;
+  using Cfg = AttnCfg;
+  constexpr int KV = Cfg::KV;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -54,7 +57,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const int qt = blockIdx.x % p.q_tiles;
   const int head = (blockIdx.x / p.q_tiles) % p.heads;
   const int n = blockIdx.x / (p.q_tiles * p.heads);
-  const int nkv = (p.T + KV - 1) / KV;
+  const int nkv = p.T / KV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
@@ -88,7 +91,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   } else if (warp == 1 && lane == 0) {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc_s = make_idesc_f16(128, KV, false, false, false);   // S[128,KV] = Q[128,64] K[KV,64]^T
-    constexpr uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);    // O[128,64] = P[128,KV] V[KV,64]
+    constexpr uint32_t idesc_o = make_idesc_f16(128, 64, false, false, true);    // O[128,64] += P[128,KV] V[KV,64]
     mbar_wait(q_full, 0);
     const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 16);
     for (int j = 0; j < nkv; ++j) {
@@ -98,94 +101,102 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       tc_fence_after();
       const uint32_t sk = smem_u32(sKV + st * 2 * Cfg::KV_BYTES);
       const uint64_t dk = make_smem_desc_sw128(sk, 1024, 16);
+      // S_j overwrites the columns P_{j-1} lived in: ordered behind PV_{j-1} by the in-order MMA pipe
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base + Cfg::COL_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
       tc_commit(s_full);
-      mbar_wait(p_full, j & 1);
+      mbar_wait(p_full, j & 1);          // P_j written and O rescaled by the softmax warps
       tc_fence_after();
       // V tile [KV rows][64 d] is an MN-major B operand: 16 kv rows (one MMA K step) = 2048 B
       const uint64_t dv = make_smem_desc_sw128(sk + Cfg::KV_BYTES, 1024, 1024);
 #pragma unroll
       for (int k = 0; k < KV / 16; ++k)
-        mma_f16_ts(tmem_base + Cfg::COL_O, tmem_base + Cfg::COL_P + 8 * k, dv + 128 * k, idesc_o, k != 0);
+        mma_f16_ts(tmem_base + Cfg::COL_O, tmem_base + Cfg::COL_P + 8 * k, dv + 128 * k, idesc_o, (j | k) != 0);
       tc_commit(&kv_empty[st]);
       tc_commit(o_full);
     }
   } else if (warp >= 2) {
-    // ------------------------------ softmax / output ------------------------------
+    // ------------------------------ softmax / correction / output ------------------------------
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // (64^-1/4)^2 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
-    float O[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) O[i] = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(KV, p.T - j * KV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // pass 1: row maximum (two 32-column loads; S is re-read in pass 2 instead of being held in 64 registers so that
+      // four CTAs fit the register file)
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < KV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, r);
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, sv);
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
       const float m_new = fmaxf(m_run, mx * kScaleLog2);
       const float alpha = exp2f(m_run - m_new);
-      // pass 2: probabilities -> fp16 -> TMEM (A operand of P V)
+      // pass 2: probabilities -> fp16 -> TMEM (A operand of P V).  P columns [c/2, c/2+16) overwrite S columns that
+      // have already been consumed by this thread (its own TMEM lane), never the half still to be read.
       float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < KV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, r);
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_S + c, sv);
         tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(r[i]) * kScaleLog2 - m_new);
-          float p1 = exp2f(__uint_as_float(r[i + 1]) * kScaleLog2 - m_new);
-          if (c + i >= kv_valid) p0 = 0.f;
-          if (c + i + 1 >= kv_valid) p1 = 0.f;
+          const float p0 = exp2f(__uint_as_float(sv[i]) * kScaleLog2 - m_new);
+          const float p1 = exp2f(__uint_as_float(sv[i + 1]) * kScaleLog2 - m_new);
           lsum += p0 + p1;
           pk[i >> 1] = pack_h2(p0, p1);
         }
         tmem_st_32x32b_x16(lane_addr + Cfg::COL_P + (c >> 1), pk);
       }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      if (j > 0) {
+        // correction: rescale the running output in place (PV_{j-1} must have landed)
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(lane_addr + Cfg::COL_O + c, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x16(lane_addr + Cfg::COL_O + c, o);
+        }
+      }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + Cfg::COL_O + c, r);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) O[c + i] = O[c + i] * alpha + __uint_as_float(r[i]);
-      }
     }
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
     const int t = qt * 128 + row;
-    if (t < p.T) {
-      const float inv = 1.0f / l_run;
-      __half* o = p.out + (static_cast<size_t>(n) * p.T + t) * p.C + head * 64;
+    const float inv = 1.0f / l_run;
+    __half* o = p.out + (static_cast<size_t>(n) * p.T + t) * p.C + head * 64;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        uint4 v;
-        v.x = pack_h2(O[i] * inv, O[i + 1] * inv);
-        v.y = pack_h2(O[i + 2] * inv, O[i + 3] * inv);
-        v.z = pack_h2(O[i + 4] * inv, O[i + 5] * inv);
-        v.w = pack_h2(O[i + 6] * inv, O[i + 7] * inv);
-        *reinterpret_cast<uint4*>(o + i) = v;
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(lane_addr + Cfg::COL_O + c, r);
+      tc_wait_ld();
+      if (t < p.T) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_h2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+          v.y = pack_h2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+          v.z = pack_h2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+          v.w = pack_h2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c + i) = v;
+        }
       }
     }
     tc_fence_before();

@@ -30,8 +30,19 @@ bool conv_can_fuse_stats(int H, int W) {
   const int TW = std::min(W, 16), TH = std::min(H, 128 / TW);
   return TW * TH >= 32;
 }
-int conv_pick_bn(int cout_pad) {
-  if (cout_pad % 256 == 0) return 256;
+int conv_pick_bn(int cout_pad, int m_tiles) {
+  if (cout_pad % 256 == 0) {
+    // Wave quantisation on the low-resolution levels (few 128-pixel tiles): a 128-wide N tile doubles the tile count at
+    // ~10% lower per-tile efficiency; take it when it shortens the predicted makespan on the 148 SMs.
+    if (m_tiles > 0) {
+      const int sms = sm_count();
+      const long t256 = static_cast<long>(m_tiles) * (cout_pad / 256), t128 = static_cast<long>(m_tiles) * (cout_pad / 128);
+      const double cost256 = static_cast<double>((t256 + sms - 1) / sms) * 1.0;
+      const double cost128 = static_cast<double>((t128 + sms - 1) / sms) * 0.72;   // half the work per tile at ~70% of the N=256 efficiency (smem-operand bound)
+      if (cost128 < cost256) return 128;
+    }
+    return 256;
+  }
   if (cout_pad % 128 == 0) return 128;
   if (cout_pad % 64 == 0) return 64;
   if (cout_pad % 16 == 0 && cout_pad <= 48) return 16;
@@ -63,7 +74,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   p.tiles_w = d.W / p.TW;
   p.tiles_h = d.H / p.TH;
   p.tiles_n = (d.N + p.TN - 1) / p.TN;
-  l->BN = conv_pick_bn(d.cout_pad);
+  l->BN = conv_pick_bn(d.cout_pad, p.tiles_w * p.tiles_h * p.tiles_n);
   p.n_blocks = d.cout_pad / l->BN;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   p.seg_chunks[0] = d.C0 / 64; p.seg_taps[0] = d.taps0;
@@ -101,6 +112,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   return l;
 }
 void conv_launch_destroy(ConvLaunch* l) { delete l; }
+int conv_launch_bn(const ConvLaunch* l) { return l->BN; }
 
 template <int BN>
 static void run_conv(const ConvLaunch* l, cudaStream_t s) {
@@ -129,7 +141,6 @@ void conv_launch_run(const ConvLaunch* l, cudaStream_t s) {
 struct AttnLaunch {
   CUtensorMap mapQ, mapKV;
   AttnParams p;
-  int KV;
   int grid;
 };
 
@@ -137,14 +148,13 @@ AttnLaunch* attn_launch_create(const void* qkv, int N, int T, int C, void* out) 
   IVID_REQUIRE(C % 64 == 0, "attention: channels must be a multiple of the head width 64");
   IVID_REQUIRE(T >= 64 && T % 64 == 0, "attention: sequence length must be a multiple of 64");
   auto* l = new AttnLaunch();
-  l->KV = (T % 128 == 0) ? 128 : 64;
   l->p.N = N; l->p.T = T; l->p.C = C; l->p.heads = C / 64;
   l->p.q_tiles = (T + 127) / 128;
   l->p.out = reinterpret_cast<__half*>(out);
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(T), static_cast<uint64_t>(N)};
   const uint64_t str[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(T) * 3 * C * 2};
   const uint32_t boxq[3] = {64, 128, 1};
-  const uint32_t boxkv[3] = {64, static_cast<uint32_t>(l->KV), 1};
+  const uint32_t boxkv[3] = {64, AttnCfg::KV, 1};
   l->mapQ = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(qkv), dims, str, boxq,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   l->mapKV = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(qkv), dims, str, boxkv,
@@ -154,19 +164,13 @@ AttnLaunch* attn_launch_create(const void* qkv, int N, int T, int C, void* out) 
 }
 void attn_launch_destroy(AttnLaunch* l) { delete l; }
 
-template <int KV>
-static void run_attn(const AttnLaunch* l, cudaStream_t s) {
+void attn_launch_run(const AttnLaunch* l, cudaStream_t s) {
   static std::once_flag once;
   std::call_once(once, [] {
-    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         AttnCfg<KV>::SMEM_BYTES));
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
   });
-  attention_kernel<KV><<<l->grid, AttnCfg<KV>::THREADS, AttnCfg<KV>::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
+  attention_kernel<<<l->grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
   IVID_CHECK_CUDA(cudaGetLastError());
-}
-void attn_launch_run(const AttnLaunch* l, cudaStream_t s) {
-  if (l->KV == 128) run_attn<128>(l, s);
-  else run_attn<64>(l, s);
 }
 
 // --------------------------------------------------------------------------------------------------

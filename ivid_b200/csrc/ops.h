@@ -30,8 +30,9 @@ struct ConvDesc {
 ConvLaunch* conv_launch_create(const ConvDesc& d);
 void conv_launch_destroy(ConvLaunch* l);
 void conv_launch_run(const ConvLaunch* l, cudaStream_t s);
+int conv_launch_bn(const ConvLaunch* l);
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s);   // same launch, output pointer overridden
-int conv_pick_bn(int cout_pad);
+int conv_pick_bn(int cout_pad, int m_tiles = 0);          // m_tiles > 0: wave-quantisation aware choice
 bool conv_can_fuse_stats(int H, int W);                    // epilogue statistics need >= 32 pixels of one sample per warp
 int conv_pad_cout(int cout);
 

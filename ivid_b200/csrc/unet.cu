@@ -499,7 +499,7 @@ Plan* Unet::build_plan(int N) {
       const double K = static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0);
       const double M = static_cast<double>(d.N) * d.H * d.W;
       static const char* names[] = {"conv_gemm<16>", "conv_gemm<64>", "conv_gemm<128>", "conv_gemm<256>"};
-      const int bn = conv_pick_bn(d.cout_pad);
+      const int bn = conv_launch_bn(l);
       pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * d.cout,
                   M * K / (d.taps0 == 9 ? 9.0 : 1.0) * 2 + M * d.cout * (d.out_mode == 1 ? 2 : 4) + K * d.cout_pad * 2,
                   std::to_string(d.H) + "x" + std::to_string(d.W) + " " + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") +
