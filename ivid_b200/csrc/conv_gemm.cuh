@@ -37,7 +37,7 @@ struct ConvGemmParams {
   const float* residual;       // fp32 NHWC or nullptr
   void* out;
   double* stats;               // optional [N][Cout][2] per-(sample, channel) sum / sum-of-squares of the output (GroupNorm)
-  int epi_tma;                 // fp32 NHWC output (and residual) moved by TMA through swizzled shared-memory tiles
+  int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
 
@@ -189,7 +189,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint64_t* res_bar = res_full + quarter * 2;
     const int box_h0 = (p.TW * p.TH >= 32) ? ((quarter * 32) / p.TW) % p.TH : 0;
     const int box_n0 = (quarter * 32) / (p.TW * p.TH);
-    const bool tma_res = p.epi_tma && p.residual != nullptr && !(p.debug & 2);
+    const bool tma_res = p.epi_tma == 1 && p.residual != nullptr && !(p.debug & 2);
     uint32_t res_cnt = 0, res_issued = 0, out_cnt = 0;
     const uint32_t my_tiles = (static_cast<int>(blockIdx.x) < p.num_tiles)
                                   ? static_cast<uint32_t>((p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) : 0u;
@@ -250,7 +250,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
           }
         }
-      } else if (p.epi_tma) {
+      } else if (p.epi_tma == 1) {
         // TMA epilogue (fp32 NHWC): per 32-column chunk the warp adds bias (+ residual tile fetched by TMA two chunks
         // ahead, across tile boundaries) in the row-per-lane layout, writes the 128B-swizzled [32 px][32 ch] tile to
         // shared memory and one lane issues a bulk tensor store; posted LSU stores from a single warp per SM
@@ -307,6 +307,79 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + col0 + lane) * 2;
               atomicAdd(st, static_cast<double>(ssum));
               atomicAdd(st + 1, static_cast<double>(qsum));
+            }
+          }
+        }
+        if (do_stats && p.TN == 1) {
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          const int t = threadIdx.x - 128;
+          for (int c = t; c < BN; c += 128) {
+            const int col = nblk * BN + c;
+            if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
+              float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
+              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
+              atomicAdd(st, static_cast<double>(ssum));
+              atomicAdd(st + 1, static_cast<double>(qsum));
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+      } else if (p.epi_tma == 2) {
+        // TMA epilogue, fp16 NHWC output (qkv projections, ResBlock hidden tensor): 64 columns per bulk store
+        // ([32 px][64 ch] fp16 = 128-byte rows); no residual on these paths.
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int k = 0; k < BN / 64; ++k) {
+          const int c0 = k * 64;
+          const int col0 = nblk * BN + c0;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + c0, r0);
+          tmem_ld_32x32b_x32(taddr + c0 + 32, r1);
+          tc_wait_ld();
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint4* ob = reinterpret_cast<uint4*>(epi_base + (out_cnt & 1) * 4096);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {          // 8 columns (16 bytes of fp16) per step
+            const uint32_t* src = jj < 4 ? r0 + 8 * jj : r1 + 8 * (jj - 4);
+            const float4 ba = ldg_f4(p.bias + col0 + 8 * jj), bb = ldg_f4(p.bias + col0 + 8 * jj + 4);
+            uint4 pk;
+            pk.x = pack_h2(__uint_as_float(src[0]) + ba.x, __uint_as_float(src[1]) + ba.y);
+            pk.y = pack_h2(__uint_as_float(src[2]) + ba.z, __uint_as_float(src[3]) + ba.w);
+            pk.z = pack_h2(__uint_as_float(src[4]) + bb.x, __uint_as_float(src[5]) + bb.y);
+            pk.w = pack_h2(__uint_as_float(src[6]) + bb.z, __uint_as_float(src[7]) + bb.w);
+            if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);
+            ob[lane * 8 + (jj ^ (lane & 7))] = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (!(p.debug & 2)) tma_store_4d(&mapOut, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
+            tma_store_commit();
+          }
+          ++out_cnt;
+          if (do_stats) {
+            // statistics of the ROUNDED tensor (exactly what the next GroupNorm will read): lane owns columns 2l, 2l+1
+            const __half2* oh = reinterpret_cast<const __half2*>(ob);
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float2 x = __half22float2(oh[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))]);
+              s0 += x.x; s1 += x.y;
+              q0 = fmaf(x.x, x.x, q0); q1 = fmaf(x.y, x.y, q1);
+            }
+            if (p.TN == 1) {
+              stat_smem[(quarter * 2 + 0) * BN + c0 + 2 * lane] = s0;
+              stat_smem[(quarter * 2 + 0) * BN + c0 + 2 * lane + 1] = s1;
+              stat_smem[(quarter * 2 + 1) * BN + c0 + 2 * lane] = q0;
+              stat_smem[(quarter * 2 + 1) * BN + c0 + 2 * lane + 1] = q1;
+            } else if (n_warp < p.N) {
+              double* st = p.stats + (static_cast<size_t>(n_warp) * p.Cout + col0 + 2 * lane) * 2;
+              atomicAdd(st, static_cast<double>(s0)); atomicAdd(st + 1, static_cast<double>(q0));
+              atomicAdd(st + 2, static_cast<double>(s1)); atomicAdd(st + 3, static_cast<double>(q1));
             }
           }
         }

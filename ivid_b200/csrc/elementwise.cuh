@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 // ----------------------------------------------------------------------------------------------
 struct GnApplyParams {
   const float* x0; const float* x1;     // fp32 NHWC sources (virtual concat along C); x1 may be null (C1 = 0)
+  const __half* x0h;                    // when non-null the (single) source is fp16 NHWC (ResBlock hidden tensor)
   int C0, C1;
   int N, H, W;                          // INPUT spatial size
   int mode;                             // 0 same, 1 up, 2 down
@@ -101,6 +102,13 @@ struct GnApplyParams {
 };
 
 __device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int w, int c, float (&v)[8]) {
+  if (p.x0h != nullptr) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.x0h + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C0 + c));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    return;
+  }
   const float* src;
   int cc, ld;
   if (c < p.C0) { src = p.x0; cc = c; ld = p.C0; } else { src = p.x1; cc = c - p.C0; ld = p.C1; }

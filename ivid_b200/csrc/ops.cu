@@ -86,7 +86,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     p.debug = dbg ? atoi(dbg) : 0;
     if (p.debug & 8) { /* 8 = no fused statistics at all */ }
   }
-  p.stats = (d.stats != nullptr && conv_can_fuse_stats(d.H, d.W) && d.out_mode == 0) ? d.stats : nullptr;
+  p.stats = (d.stats != nullptr && conv_can_fuse_stats(d.H, d.W) && d.out_mode != 2) ? d.stats : nullptr;
   IVID_REQUIRE(d.stats == nullptr || p.stats != nullptr, "conv: fused statistics need >= 32 pixels per sample per warp");
   IVID_REQUIRE(d.out_mode == 2 || (d.cout % 8 == 0 && d.ldc % 8 == 0), "conv: NHWC output needs Cout % 8 == 0");
   const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0);
@@ -107,7 +107,16 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     l->mapOut = f32_map(d.out, d.ldc);
     if (d.residual != nullptr) l->mapRes = f32_map(d.residual, d.ldr);
     p.epi_tma = 1;
+  } else if (d.out_mode == 1 && l->BN >= 64 && d.cout % 64 == 0 && d.residual == nullptr && !(p.debug & 16)) {
+    const int bh = std::min(p.TH, 32 / p.TW), bn = 32 / (p.TW * bh);
+    const uint64_t dims[4] = {static_cast<uint64_t>(d.ldc), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.N)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d.ldc) * 2, static_cast<uint64_t>(d.W) * d.ldc * 2, static_cast<uint64_t>(d.H) * d.W * d.ldc * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    l->mapOut = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    p.epi_tma = 2;
   }
+  // fused statistics are produced by the TMA epilogues only
+  if (p.stats != nullptr && p.epi_tma == 0) throw Error(kErrInvalidArgument, "conv: fused statistics need a TMA epilogue (Cout % 64 == 0)");
   l->grid = std::min(p.num_tiles, sm_count());
   return l;
 }
@@ -196,6 +205,8 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   IVID_REQUIRE(d.stats0 != nullptr && d.gamma != nullptr && d.beta != nullptr, "gn_apply: statistics / affine parameters missing");
   GnApplyParams p;
   p.x0 = d.x0; p.x1 = d.x1; p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
+  p.x0h = d.x0_half ? reinterpret_cast<const __half*>(d.x0) : nullptr;
+  IVID_REQUIRE(!d.x0_half || d.C1 == 0, "gn_apply: fp16 source cannot be part of a concat");
   p.silu = d.silu;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
@@ -204,7 +215,13 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
   const int Wo = d.mode == 1 ? d.W * 2 : (d.mode == 2 ? d.W / 2 : d.W);
   // ~8K work items (8 channels each) per block; at least one pixel
-  p.pix_per_block = std::max(1, std::min(Ho * Wo, 8192 / (C / 8)));
+  // One wave of blocks (3 resident per SM) split evenly over the samples, so the statistics -> coefficient prologue is
+  // paid once per ~1/13th of an image instead of once per 8K work items; never less than 8K items per block.
+  {
+    const int blocks_per_n = std::max(1, (sm_count() * 3) / std::max(d.N, 1));
+    const int by_wave = (Ho * Wo + blocks_per_n - 1) / blocks_per_n;
+    p.pix_per_block = std::max(1, std::min(Ho * Wo, std::max(by_wave, 8192 / (C / 8))));
+  }
   dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;
   gn_apply_kernel<<<grid, 256, smem, s>>>(p);

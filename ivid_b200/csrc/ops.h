@@ -43,6 +43,7 @@ void attn_launch_run(const AttnLaunch* l, cudaStream_t s);
 void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaStream_t s);
 struct GnApplyDesc {
   const float* x0 = nullptr; const float* x1 = nullptr; int C0 = 0, C1 = 0;
+  bool x0_half = false;                                            // x0 points at fp16 data (C1 must be 0)
   int N = 0, H = 0, W = 0; int mode = 0; int silu = 1;
   const double* stats0 = nullptr; const double* stats1 = nullptr;   // per-(sample, channel) sum / sumsq of each source
   int groups = 32; float eps = 1e-5f;

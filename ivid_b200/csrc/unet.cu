@@ -601,20 +601,24 @@ Plan* Unet::build_plan(int N) {
       IVID_REQUIRE(!(r.skip_conv && r.mode != 0), "internal: up/down ResBlocks keep the channel count");
       add_apply(g1);
       // conv1 -> h (fp32) ; stats
+      bool h_half = false;
       Act h; h.C = r.cout; h.H = Ho; h.W = Wo; h.data = s_h;
       h.stats = take_stats(r.cout);
       {
         ConvDesc d;
         d.act0 = s_a1; d.C0 = r.cin; d.taps0 = 9;
         d.weight = W8(r.conv1.w_off); d.cout_pad = r.conv1.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv1.b_off);
-        d.out = h.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
+        // the hidden tensor only feeds GroupNorm 2: stored as fp16 (half the epilogue and GN traffic); its statistics are
+        // taken from the rounded values in the conv epilogue.  Tiny feature maps keep the fp32 + stats-kernel path.
+        h_half = conv_can_fuse_stats(Ho, Wo);
+        d.out = h.data; d.ldc = r.cout; d.out_mode = h_half ? 1 : 0; d.N = N; d.H = Ho; d.W = Wo;
         add_conv(d, &h);
         add_stats(h);
       }
       // GN2 * (1+scale) + shift, SiLU -> a2
       add_coeff(h, nullptr, r.gn2, r.film_off);
       GnApplyDesc g2;
-      g2.x0 = h.data; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1;
+      g2.x0 = h.data; g2.x0_half = h_half; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1;
       g2.out_act = s_a2;
       add_apply(g2);
       // conv2 (+ 1x1 skip as extra K) + residual -> out

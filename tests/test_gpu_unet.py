@@ -52,7 +52,8 @@ def test_layerwise_taps_tiny(golden):
     assert G.report("tiny seed99 N=1", net(x.cuda(), t.cuda(), c.cuda()), ref) < EPS_TOL
 
 
-@pytest.mark.parametrize("name,N", [("rgbd_singlecategory_adm_128_small", 1), ("rgbd_imagenet_adm_128_large_cfg", 2)])
+@pytest.mark.parametrize("name,N", [("rgbd_singlecategory_adm_128_small", 1), ("rgbd_imagenet_adm_128_large_cfg", 2),
+                                    ("rgbd_imagenet_adm_128_large_cond", 1), ("rgbd_imagenet_adm_256_128_small_sr", 1)])
 def test_real_config_vs_oracle(golden, name, N):
     cfg = json.loads(bytes(golden[f"schemacfg_{name}"]).decode())
     sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
