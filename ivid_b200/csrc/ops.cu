@@ -220,7 +220,9 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   {
     const int blocks_per_n = std::max(1, (sm_count() * 3) / std::max(d.N, 1));
     const int by_wave = (Ho * Wo + blocks_per_n - 1) / blocks_per_n;
-    p.pix_per_block = std::max(1, std::min(Ho * Wo, std::max(by_wave, 8192 / (C / 8))));
+    static const int mode = getenv("IVID_GN_BLOCK") ? atoi(getenv("IVID_GN_BLOCK")) : 1;
+    const int small = 8192 / (C / 8);
+    p.pix_per_block = std::max(1, std::min(Ho * Wo, mode == 0 ? small : (mode == 2 ? std::max(by_wave / 4, small) : std::max(by_wave, small))));
   }
   dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;

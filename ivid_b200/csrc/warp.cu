@@ -132,32 +132,105 @@ struct RasterParams {
   int nviews, F, S;
 };
 
-__device__ __forceinline__ void raster_one(const WVtx* v, int S, unsigned long long* vis, uint32_t prim) {
+// One set-up sub-triangle, flattened to 32-bit words so a lane can broadcast it to its warp with shuffles.
+struct RTri {
+  long long X[3], Y[3];
+  float zw[3], iw[3], pad[3];
+  long long area;
+  int px0, px1, py0, py1;
+  uint32_t prim;
+  int valid;
+};
+constexpr int kRTriWords = sizeof(RTri) / 4;
+
+__device__ __forceinline__ void rtri_make(const WVtx* v, int S, uint32_t prim, RTri& r) {
   TriSetup t;
   tri_setup(v, S, t);
+  r.valid = 0;
   if (t.area == 0) return;
-  const bool front = t.area > 0;
-  long long minx = min(t.X[0], min(t.X[1], t.X[2])), maxx = max(t.X[0], max(t.X[1], t.X[2]));
-  long long miny = min(t.Y[0], min(t.Y[1], t.Y[2])), maxy = max(t.Y[0], max(t.Y[1], t.Y[2]));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { r.X[i] = t.X[i]; r.Y[i] = t.Y[i]; r.zw[i] = t.zw[i]; r.iw[i] = t.iw[i]; r.pad[i] = v[i].pad; }
+  r.area = t.area;
+  r.prim = prim;
+  const long long minx = min(t.X[0], min(t.X[1], t.X[2])), maxx = max(t.X[0], max(t.X[1], t.X[2]));
+  const long long miny = min(t.Y[0], min(t.Y[1], t.Y[2])), maxy = max(t.Y[0], max(t.Y[1], t.Y[2]));
   if (maxx < 128 || maxy < 128) return;
   long long px0 = minx <= 128 ? 0 : (minx - 128 + 255) / 256, px1 = (maxx - 128) / 256;
   long long py0 = miny <= 128 ? 0 : (miny - 128 + 255) / 256, py1 = (maxy - 128) / 256;
   if (px1 > S - 1) px1 = S - 1;
   if (py1 > S - 1) py1 = S - 1;
-  for (long long py = py0; py <= py1; ++py) {
-    for (long long px = px0; px <= px1; ++px) {
-      float l0, l1, l2;
-      if (!tri_eval(t, px, py, l0, l1, l2)) continue;
-      const float z = (l0 * t.zw[0] + l1 * t.zw[1]) + l2 * t.zw[2];
-      if (!(z > 0.f && z < 1.f)) continue;
-      if (!front) {
-        const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
-        const float bs = (b0 + b1) + b2;
-        const float pad = ((b0 / bs) * v[0].pad + (b1 / bs) * v[1].pad) + (b2 / bs) * v[2].pad;
-        if (pad > 0.001f) continue;      // back-facing frustum padding is discarded (aggregation.fsh:23)
+  if (px0 > px1 || py0 > py1) return;
+  r.px0 = static_cast<int>(px0); r.px1 = static_cast<int>(px1); r.py0 = static_cast<int>(py0); r.py1 = static_cast<int>(py1);
+  r.valid = 1;
+}
+
+__device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis) {
+  TriSetup t;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { t.X[i] = r.X[i]; t.Y[i] = r.Y[i]; t.zw[i] = r.zw[i]; t.iw[i] = r.iw[i]; }
+  t.area = r.area;
+  float l0, l1, l2;
+  if (!tri_eval(t, px, py, l0, l1, l2)) return;
+  const float z = (l0 * t.zw[0] + l1 * t.zw[1]) + l2 * t.zw[2];
+  if (!(z > 0.f && z < 1.f)) return;
+  if (!(r.area > 0)) {
+    const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
+    const float bs = (b0 + b1) + b2;
+    const float pad = ((b0 / bs) * r.pad[0] + (b1 / bs) * r.pad[1]) + (b2 / bs) * r.pad[2];
+    if (pad > 0.001f) return;      // back-facing frustum padding is discarded (aggregation.fsh:23)
+  }
+  const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | r.prim;
+  atomicMin(vis + static_cast<size_t>(py) * S + px, key);
+}
+
+// Small triangles (the common 3x3-pixel case) are scanned by their own lane; triangles with a large bounding box (the
+// frustum ring and faces stretched across depth discontinuities) are broadcast to the warp and scanned by all 32 lanes.
+__device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane) {
+  constexpr int kSmall = 48;
+  const int w = r.valid ? (r.px1 - r.px0 + 1) : 0, h = r.valid ? (r.py1 - r.py0 + 1) : 0;
+  const bool big = r.valid && (w * h > kSmall);
+  if (r.valid && !big) {
+    for (int py = r.py0; py <= r.py1; ++py)
+      for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis);
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, big);
+  while (mask) {
+    const int leader = __ffs(mask) - 1;
+    mask &= mask - 1;
+    RTri b;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&r);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+    for (int i = 0; i < kRTriWords; ++i) dst[i] = __shfl_sync(0xffffffffu, src[i], leader);
+    // 8x8-pixel tiles of the bounding box; a tile is skipped when one edge function is negative at its most-inside
+    // corner (exact integer test, so the surviving pixels are decided by the same arithmetic as the small path)
+    const long long sgn = b.area > 0 ? 1 : -1;
+    long long ea[3], eb[3], ec[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int a = (i + 1) % 3, c = (i + 2) % 3;
+      ea[i] = -(b.Y[c] - b.Y[a]) * sgn;
+      eb[i] = (b.X[c] - b.X[a]) * sgn;
+      ec[i] = -(ea[i] * b.X[a] + eb[i] * b.Y[a]);
+    }
+    const int tx0 = b.px0 >> 3, tx1 = b.px1 >> 3, ty0 = b.py0 >> 3, ty1 = b.py1 >> 3;
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int x0 = max(tx * 8, b.px0), x1 = min(tx * 8 + 7, b.px1), y0 = max(ty * 8, b.py0), y1 = min(ty * 8 + 7, b.py1);
+        const long long cx0 = static_cast<long long>(x0) * 256 + 128, cx1 = static_cast<long long>(x1) * 256 + 128;
+        const long long cy0 = static_cast<long long>(y0) * 256 + 128, cy1 = static_cast<long long>(y1) * 256 + 128;
+        bool out = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const long long emax = ea[i] * (ea[i] > 0 ? cx1 : cx0) + eb[i] * (eb[i] > 0 ? cy1 : cy0) + ec[i];
+          out = out || (emax < 0);
+        }
+        if (out) continue;
+        for (int idx = lane; idx < 64; idx += 32) {
+          const int px = tx * 8 + (idx & 7), py = ty * 8 + (idx >> 3);
+          if (px >= x0 && px <= x1 && py >= y0 && py <= y1) rtri_pixel(b, px, py, S, vis);
+        }
       }
-      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(z)) << 32) | prim;
-      atomicMin(vis + py * S + px, key);
     }
   }
 }
@@ -165,19 +238,28 @@ __device__ __forceinline__ void raster_one(const WVtx* v, int S, unsigned long l
 __global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int view = blockIdx.y, b = blockIdx.z;
-  if (f >= p.F) return;
-  const ViewRef vr = p.views[b * p.nviews + view];
-  const float* mvp = p.mvp + b * 16;
-  WVtx in[3], poly[4];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[f * 3 + k], mvp, in[k]);
-  const int n = clip_near(in, poly);
+  const int lane = threadIdx.x & 31;
   unsigned long long* vis = p.vis + (static_cast<size_t>(b) * p.nviews + view) * p.S * p.S;
-  if (n >= 3) raster_one(poly, p.S, vis, static_cast<uint32_t>(f) * 2u);
-  if (n == 4) {
-    WVtx t1[3] = {poly[0], poly[2], poly[3]};
-    raster_one(t1, p.S, vis, static_cast<uint32_t>(f) * 2u + 1u);
+  RTri t0, t1;
+  t0.valid = 0; t1.valid = 0;
+  if (f < p.F) {
+    // faces are visited in a permuted order (7919 is coprime to the face count of any (n+1)^2*2 grid used here) so that
+    // the runs of large triangles (frustum ring rows) spread over all warps; primitive ids stay the face indices
+    const int fi = static_cast<int>((static_cast<long long>(f) * 7919) % p.F);
+    const ViewRef vr = p.views[b * p.nviews + view];
+    const float* mvp = p.mvp + b * 16;
+    WVtx in[3], poly[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[fi * 3 + k], mvp, in[k]);
+    const int n = clip_near(in, poly);
+    if (n >= 3) rtri_make(poly, p.S, static_cast<uint32_t>(fi) * 2u, t0);
+    if (n == 4) {
+      WVtx q[3] = {poly[0], poly[2], poly[3]};
+      rtri_make(q, p.S, static_cast<uint32_t>(fi) * 2u + 1u, t1);
+    }
   }
+  rtri_raster(t0, p.S, vis, lane);
+  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
