@@ -162,7 +162,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   const int npix = min(p.pix_per_block, Ho * Wo - pix0);
   const int items = npix * c8;
   int it0 = threadIdx.x;
-  if (p.mode == 0) {
+  if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
+    // fp16 source (ResBlock hidden tensor): 8 work items per trip kept packed (4 registers each) until consumed, so a
+    // thread still has 128 bytes of reads in flight although each item is only 16 bytes
+    constexpr int U = 8;
+    for (; it0 + (U - 1) * 256 < items; it0 += U * 256) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * 256;
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(p.x0h + (static_cast<size_t>(n) * Ho * Wo + pix0 + it / c8) * C + (it % c8) * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * 256;
+        const int cg = it % c8;
+        const size_t o = (static_cast<size_t>(n) * Ho * Wo + pix0 + it / c8) * C + cg * 8;
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          float y0 = fmaf(f.x, s_ab[(2 * j) * c8 + cg], s_ab[C + (2 * j) * c8 + cg]);
+          float y1 = fmaf(f.y, s_ab[(2 * j + 1) * c8 + cg], s_ab[C + (2 * j + 1) * c8 + cg]);
+          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+          pk[j] = pack_h2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(p.out_act + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  } else if (p.mode == 0) {
     // same-resolution fast path (the bulk of the traffic): 4 work items per thread per trip, all 8 x 16-byte loads issued
     // before any is consumed, so a block keeps ~32 KB of reads in flight
     constexpr int U = 4;

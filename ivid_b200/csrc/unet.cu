@@ -335,6 +335,7 @@ void Unet::finalize(int device) {
 }
 
 Unet::~Unet() {
+  if (side_stream_) { cudaStreamDestroy(side_stream_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_join_); }
   plans_.clear();
   if (arena_) cudaFree(arena_);
 }
@@ -344,6 +345,7 @@ Unet::~Unet() {
 // ==================================================================================================
 struct Plan {
   int N = 0;
+  int slot = 0;            // 0 = main stream, 1 = side stream (two half-batches run concurrently)
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
   double* stats_base = nullptr;
@@ -395,10 +397,14 @@ struct Bump {
 };
 }  // namespace
 
-Plan* Unet::get_plan(int N) {
-  for (auto& p : plans_) if (p->N == N) return p.get();
-  if (plans_.size() >= 3) plans_.erase(plans_.begin());
+Plan* Unet::get_plan(int N, int slot) {
+  for (auto& p : plans_) if (p->N == N && p->slot == slot) return p.get();
+  if (plans_.size() >= 4) {
+    IVID_CHECK_CUDA(cudaDeviceSynchronize());     // the evicted plan's workspace may still be in use by queued kernels
+    plans_.erase(plans_.begin());
+  }
   plans_.emplace_back(build_plan(N));
+  plans_.back()->slot = slot;
   return plans_.back().get();
 }
 
@@ -534,7 +540,9 @@ Plan* Unet::build_plan(int N) {
         const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
         const double in_el = static_cast<double>(d.N) * d.H * d.W * (d.C0 + d.C1);
         const double out_el = static_cast<double>(d.N) * Ho * Ho * (d.C0 + d.C1);
-        pl->ops.tag("gn_apply", 0, in_el * 4 + out_el * 2 + (d.out_raw16 ? out_el * 2 : 0) + (d.out_raw32 ? out_el * 4 : 0));
+        pl->ops.tag("gn_apply", 0, in_el * (d.x0_half ? 2 : 4) + out_el * 2 + (d.out_raw16 ? out_el * 2 : 0) + (d.out_raw32 ? out_el * 4 : 0),
+                    std::to_string(d.H) + "x" + std::to_string(d.W) + " C" + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") +
+                        " m" + std::to_string(d.mode) + (d.x0_half ? " h16" : "") + (d.out_raw16 ? " raw16" : "") + (d.out_raw32 ? " raw32" : ""));
       }
       pl->ops.push_back([d](cudaStream_t s) { launch_gn_apply(d, s); });
     };
@@ -728,11 +736,59 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   // reference: "this model is not class-conditioned" (adm.py:540)
   IVID_REQUIRE(classes == nullptr || cfg_.num_classes > 0, "this model is not class-conditioned");
   IVID_CHECK_CUDA(cudaSetDevice(device_));
-  Plan* pl = get_plan(N);
-  pl->x = x; pl->Nx = Nx; pl->t = t; pl->classes = classes; pl->eps = eps;
-  if (cond) pl->cond = *cond; else pl->cond = ivid_cond_t{};
-  const int expect_in = pl->cond.kind == 1 ? (pl->cond.mask_rgb_dev ? 10 : 9) : (pl->cond.kind == 2 ? 8 : cfg_.in_channels);
+  ivid_cond_t cnd = cond ? *cond : ivid_cond_t{};
+  const int expect_in = cnd.kind == 1 ? (cnd.mask_rgb_dev ? 10 : 9) : (cnd.kind == 2 ? 8 : cfg_.in_channels);
   IVID_REQUIRE(expect_in == cfg_.in_channels, "forward: conditional inputs do not match the model's in_channels");
+
+  // Two half-batches on two streams: the HBM-bound GroupNorm passes of one half overlap the tensor-bound convolutions
+  // of the other (a persistent conv CTA leaves enough registers / shared memory on every SM for a gn_apply block).
+  // The halves are independent samples (typically the two classifier-free-guidance halves sharing x).
+  // Measured on B200 (api.cu: ivid_debug_overlap): the two kernels do NOT overlap today (conv alone 0.21 ms + gn alone
+  // 0.08 ms = 0.28 ms when issued concurrently), so the split is opt-in (IVID_SPLIT_BATCH=1) until the co-residency
+  // blocker is understood.
+  static const bool split_ok = getenv("IVID_SPLIT_BATCH") != nullptr;
+  const bool can_split = split_ok && !profile_ && N % 2 == 0 && N >= 4 && (Nx == N || Nx == N / 2) &&
+                         !(cnd.kind != 0 && Nx == N && cnd.noise_dev == nullptr);
+  if (can_split) {
+    const int half = N / 2;
+    const size_t img = static_cast<size_t>(cfg_.image_size) * cfg_.image_size;
+    if (side_stream_ == nullptr) {
+      IVID_CHECK_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+      IVID_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+      IVID_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+    }
+    IVID_CHECK_CUDA(cudaEventRecord(ev_fork_, stream));
+    IVID_CHECK_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+    for (int hb = 0; hb < 2; ++hb) {
+      Plan* ph = get_plan(half, hb);
+      cudaStream_t st = hb == 0 ? stream : side_stream_;
+      const bool shift = (Nx == N) && hb == 1;            // rows [half, N) of per-sample inputs
+      const size_t xs = static_cast<size_t>(cfg_.in_channels) * img;
+      ph->x = x + (shift && cnd.kind == 0 ? static_cast<size_t>(half) * xs : 0);
+      if (cnd.kind != 0) ph->x = x + (shift ? static_cast<size_t>(half) * cfg_.out_channels * img : 0);
+      ph->Nx = half;
+      ph->t = t + hb * half;
+      ph->classes = classes ? classes + hb * half : nullptr;
+      ph->eps = eps + static_cast<size_t>(hb) * half * cfg_.out_channels * img;
+      ph->cond = cnd;
+      if (cnd.kind != 0 && shift) {
+        const size_t yimg = cnd.kind == 2 ? img / 4 : img;
+        ph->cond.y_dev = cnd.y_dev + static_cast<size_t>(half) * 4 * yimg;
+        if (cnd.mask_dev) ph->cond.mask_dev = cnd.mask_dev + static_cast<size_t>(half) * img;
+        if (cnd.mask_rgb_dev) ph->cond.mask_rgb_dev = cnd.mask_rgb_dev + static_cast<size_t>(half) * img;
+        if (cnd.noise_dev) ph->cond.noise_dev = cnd.noise_dev + static_cast<size_t>(half) * 4 * img;
+      }
+      IVID_CHECK_CUDA(cudaMemsetAsync(ph->stats_base, 0, ph->stats_bytes, st));
+      for (auto& op : ph->ops.v) op.fn(st);
+    }
+    IVID_CHECK_CUDA(cudaEventRecord(ev_join_, side_stream_));
+    IVID_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_join_, 0));
+    return;
+  }
+
+  Plan* pl = get_plan(N, 0);
+  pl->x = x; pl->Nx = Nx; pl->t = t; pl->classes = classes; pl->eps = eps;
+  pl->cond = cnd;
   IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
   if (!profile_) {
     for (auto& op : pl->ops.v) op.fn(stream);
@@ -754,7 +810,8 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
     agg.launches += 1; agg.ms += ms; agg.flops += pl->ops.v[i].flops; agg.bytes += pl->ops.v[i].bytes;
     if (!pl->ops.v[i].note.empty()) {
       char buf[256];
-      snprintf(buf, sizeof(buf), "[\"%s\", \"%s\", %.5f, %.4e]", pl->ops.v[i].label, pl->ops.v[i].note.c_str(), ms, pl->ops.v[i].flops);
+      snprintf(buf, sizeof(buf), "[\"%s\", \"%s\", %.5f, %.4e, %.4e]", pl->ops.v[i].label, pl->ops.v[i].note.c_str(), ms, pl->ops.v[i].flops,
+               pl->ops.v[i].bytes);
       if (!profile_ops_.empty()) profile_ops_ += ", ";
       profile_ops_ += buf;
     }

@@ -88,7 +88,7 @@ class Unet {
   void build_topology();
   int add_param(const std::string& name, std::vector<int64_t> shape, bool is_buffer = false);
   const ParamSpec& P(const std::string& name) const;
-  Plan* get_plan(int N);
+  Plan* get_plan(int N, int slot);
   Plan* build_plan(int N);
 
   UnetConfig cfg_;
@@ -111,6 +111,8 @@ class Unet {
   size_t arena_bytes_ = 0;
   int device_ = -1;
 
+  cudaStream_t side_stream_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   struct ProfAgg { int launches = 0; double ms = 0, flops = 0, bytes = 0; };
   bool profile_ = false;
   std::map<std::string, ProfAgg> profile_acc_;

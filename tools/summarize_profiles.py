@@ -37,8 +37,9 @@ if os.path.exists(p):
     print(f"wrote profiles/launches_{tag}_summary.csv ({sum(v[0] for v in agg.values())} launches, {tot / 1e3:.2f} ms)")
 
 # ---- full capture: the metrics the roofline quotes ----
-rep = f"gpurun_out/prof_{tag}.ncu-rep"
-if os.path.exists(rep):
+import glob
+for rep in sorted(glob.glob(f"gpurun_out/prof_{tag}*.ncu-rep")):
+    suffix = os.path.basename(rep)[len(f"prof_{tag}"):-len(".ncu-rep")]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -53,5 +54,5 @@ if os.path.exists(rep):
     res = []
     for r in rows[2:]:
         res.append({k: (r[i] + (" " + units[i] if units[i] else "")) for k, i in idx})
-    json.dump(res, open(f"profiles/ncu_full_{tag}_summary.json", "w"), indent=1)
-    print(f"wrote profiles/ncu_full_{tag}_summary.json ({len(res)} kernels)")
+    json.dump(res, open(f"profiles/ncu_full_{tag}{suffix}_summary.json", "w"), indent=1)
+    print(f"wrote profiles/ncu_full_{tag}{suffix}_summary.json ({len(res)} kernels)")
