@@ -41,14 +41,17 @@ struct ConvGemmParams {
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
 
-template <int BN>
+// kCtas == 2: a CTA pair (cluster of 2, one TPC) computes a 256-pixel x BN tile with tcgen05.mma.cta_group::2 — each CTA
+// stages its own 128 pixels of A and HALF of the weight tile, which cuts the L2 -> shared-memory operand traffic per
+// FLOP by a third and the per-stage footprint to 32 KB (4 stages + the TMA epilogue buffers fit in 227 KB).
+template <int BN, int kCtas = 1>
 struct ConvGemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / kCtas) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128) ? 4 : (BN == 64) ? 5 : 6;
+  static constexpr int STAGES = (kCtas == 2) ? 4 : (BN == 256) ? 3 : (BN == 128) ? 4 : (BN == 64) ? 5 : 6;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAT_BYTES = 8 * BN * 4;                                // [4 warps][sum|sumsq][BN] fp32
@@ -58,13 +61,14 @@ struct ConvGemmCfg {
   static constexpr int THREADS = 256;
 };
 
-template <int BN>
+template <int BN, int kCtas = 1>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN>;
+  using Cfg = ConvGemmCfg<BN, kCtas>;
   constexpr int STAGES = Cfg::STAGES;
+  const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;            // 1024-aligned (TMA 128B swizzle)
@@ -92,16 +96,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], 4 * kCtas);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();      // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // work items of this CTA: tiles (kCtas == 1) or tile PAIRS of its cluster (kCtas == 2; CTA `rank` owns m-tile 2*pair+rank)
+  const int w_first = (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int w_stride = (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int w_limit = p.num_tiles / kCtas;
 
   const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1];
   const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -110,9 +122,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // ===================================== TMA producer =====================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nblk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+    // 2-CTA: every load of either CTA signals the LEADER's full barrier (its MMA thread consumes both halves)
+    const uint32_t full0 = (kCtas == 2) ? mapa_cluster(smem_u32(&full_bar[0]), 0) : 0u;
+    for (int w = w_first; w < w_limit; w += w_stride) {
+      const int nblk = w % p.n_blocks;
+      const int mt = (w / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
       const int tn = mt / tiles_per_img;
       const int rem = mt - tn * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -134,23 +148,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-            tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, w0 + dx, h0 + dy, n0);
-            tma_load_2d(&mapB, &full_bar[stage], sb, kcol, nblk * BN);
+            if constexpr (kCtas == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+              const uint32_t bar = full0 + stage * 8;
+              tma_load_4d_2sm(mapA, bar, sa, ch * 64, w0 + dx, h0 + dy, n0);
+              tma_load_2d_2sm(&mapB, bar, sb, kcol, nblk * BN + static_cast<int>(cta_rank) * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+              tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, w0 + dx, h0 + dy, n0);
+              tma_load_2d(&mapB, &full_bar[stage], sb, kcol, nblk * BN);
+            }
             kcol += 64;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================== MMA issuer =====================================
-    constexpr uint32_t idesc = make_idesc_f16(128, BN, false, false, false);
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ===================================== MMA issuer (leader CTA only in 2-CTA mode) =====================================
+    constexpr uint32_t idesc = make_idesc_f16(128 * kCtas, BN, false, false, false);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int w = w_first; w < w_limit; w += w_stride) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -165,12 +186,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-          mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (kCtas == 2) mma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          else mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        tc_commit(&empty_bar[stage]);   // frees the smem slot once the MMAs above have consumed it
+        // frees the smem slot (in both CTAs) once the MMAs above have consumed it
+        if constexpr (kCtas == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+      // accumulator complete -> epilogue (of both CTAs)
+      if constexpr (kCtas == 2) tc_commit_2sm(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -191,13 +215,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int box_n0 = (quarter * 32) / (p.TW * p.TH);
     const bool tma_res = p.epi_tma == 1 && p.residual != nullptr && !(p.debug & 2);
     uint32_t res_cnt = 0, res_issued = 0, out_cnt = 0;
-    const uint32_t my_tiles = (static_cast<int>(blockIdx.x) < p.num_tiles)
-                                  ? static_cast<uint32_t>((p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) : 0u;
+    const uint32_t my_tiles = (w_first < w_limit) ? static_cast<uint32_t>((w_limit - w_first + w_stride - 1) / w_stride) : 0u;
     const uint32_t total_seq = my_tiles * NCH;
     auto issue_res = [&](uint32_t seq) {      // lane 0: residual tile of chunk `seq` of this CTA's chunk stream
-      const int t2 = static_cast<int>(blockIdx.x) + static_cast<int>(seq / NCH) * static_cast<int>(gridDim.x);
+      const int w2 = w_first + static_cast<int>(seq / NCH) * w_stride;
       const int k2 = static_cast<int>(seq % NCH);
-      const int nblk2 = t2 % p.n_blocks, mt2 = t2 / p.n_blocks;
+      const int nblk2 = w2 % p.n_blocks, mt2 = (w2 / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
       const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
       uint64_t* bar = &res_bar[seq & 1];
@@ -211,9 +234,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         res_issued = total_seq < 2 ? total_seq : 2;
       }
     }
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nblk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
+    const uint32_t tmem_empty0 = (kCtas == 2) ? mapa_cluster(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int wi = w_first; wi < w_limit; wi += w_stride) {
+      const int nblk = wi % p.n_blocks;
+      const int mt = (wi / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
       const int tn = mt / tiles_per_img;
       const int rem = mt - tn * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -521,17 +545,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_cluster(tmem_empty0 + acc * 8);      // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.epi_tma && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();      // the peer's smem / TMEM stay alive until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -20,6 +20,7 @@ struct ConvLaunch {
   ConvGemmParams p;
   int BN;
   int grid;
+  int ctas = 1;          // 2 = CTA-pair kernel (cluster of 2, cta_group::2 MMA)
 };
 
 int conv_pad_cout(int cout) {
@@ -53,8 +54,8 @@ template <int BN>
 static void set_conv_attr() {
   static std::once_flag once;
   std::call_once(once, [] {
-    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ConvGemmCfg<BN>::SMEM_BYTES));
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvGemmCfg<BN, 1>::SMEM_BYTES));
   });
 }
 
@@ -92,7 +93,13 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0);
   l->mapA0 = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
   l->mapA1 = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : l->mapA0;
-  l->mapB = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN);
+  // CTA pairs for the wide tiles: needs an even number of pixel tiles (the pair splits two adjacent ones)
+  {
+    static const bool pair_ok = getenv("IVID_NO_2CTA") == nullptr;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    l->ctas = (pair_ok && l->BN == 256 && m_tiles % 2 == 0 && m_tiles >= 2) ? 2 : 1;
+  }
+  l->mapB = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / l->ctas);
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
   l->mapOut = l->mapA0; l->mapRes = l->mapA0;
   p.epi_tma = 0;
@@ -117,7 +124,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   }
   // fused statistics are produced by the TMA epilogues only
   if (p.stats != nullptr && p.epi_tma == 0) throw Error(kErrInvalidArgument, "conv: fused statistics need a TMA epilogue (Cout % 64 == 0)");
-  l->grid = std::min(p.num_tiles, sm_count());
+  l->grid = l->ctas == 2 ? 2 * std::min(p.num_tiles / 2, sm_count() / 2) : std::min(p.num_tiles, sm_count());
   return l;
 }
 void conv_launch_destroy(ConvLaunch* l) { delete l; }
@@ -126,9 +133,27 @@ int conv_launch_bn(const ConvLaunch* l) { return l->BN; }
 template <int BN>
 static void run_conv(const ConvLaunch* l, cudaStream_t s) {
   set_conv_attr<BN>();
-  conv_gemm_kernel<BN><<<l->grid, ConvGemmCfg<BN>::THREADS, ConvGemmCfg<BN>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1, l->mapB,
-                                                                                                l->mapOut, l->mapRes, l->p);
+  conv_gemm_kernel<BN, 1><<<l->grid, ConvGemmCfg<BN, 1>::THREADS, ConvGemmCfg<BN, 1>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1, l->mapB,
+                                                                                                      l->mapOut, l->mapRes, l->p);
   IVID_CHECK_CUDA(cudaGetLastError());
+}
+static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
+  using Cfg = ConvGemmCfg<256, 2>;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(l->grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->mapA0, l->mapA1, l->mapB, l->mapOut, l->mapRes, l->p));
 }
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {
   ConvLaunch tmp = *l;
@@ -136,6 +161,7 @@ void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {
   conv_launch_run(&tmp, s);
 }
 void conv_launch_run(const ConvLaunch* l, cudaStream_t s) {
+  if (l->ctas == 2) { run_conv_pair(l, s); return; }
   switch (l->BN) {
     case 256: run_conv<256>(l, s); break;
     case 128: run_conv<128>(l, s); break;
