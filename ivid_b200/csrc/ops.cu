@@ -240,14 +240,13 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.out_raw32 = d.out_raw32;
   const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
   const int Wo = d.mode == 1 ? d.W * 2 : (d.mode == 2 ? d.W / 2 : d.W);
-  // ~8K work items (8 channels each) per block; at least one pixel
   // One wave of blocks (3 resident per SM) split evenly over the samples, so the statistics -> coefficient prologue is
-  // paid once per ~1/13th of an image instead of once per 8K work items; never less than 8K items per block.
+  // paid once per ~1/13th of an image; small tensors still spread over all SMs (>= 1K work items per block).
   {
     const int blocks_per_n = std::max(1, (sm_count() * 3) / std::max(d.N, 1));
     const int by_wave = (Ho * Wo + blocks_per_n - 1) / blocks_per_n;
     static const int mode = getenv("IVID_GN_BLOCK") ? atoi(getenv("IVID_GN_BLOCK")) : 1;
-    const int small = 8192 / (C / 8);
+    const int small = std::max(1, 1024 / (C / 8));      // at least ~4 work items per thread
     p.pix_per_block = std::max(1, std::min(Ho * Wo, mode == 0 ? small : (mode == 2 ? std::max(by_wave / 4, small) : std::max(by_wave, small))));
   }
   dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
