@@ -50,3 +50,22 @@ def test_sample_all_two_views(golden):
     assert cond.shape == (1, 7, 32, 32) and torch.isfinite(cond).all()
     assert torch.all(cond[:, 5] <= cond[:, 4]), 'mask_rgb is a subset of mask (utils.py:464)'
     assert torch.all((cond[:, 4] == 0) | (cond[:, 4] == 1))
+
+
+def test_large_models_two_view_pipeline(golden):
+    """BASELINE config 3 shape at reduced step counts: rgbd_imagenet_adm_128_large_cfg (uncond, DDIM 6 steps) ->
+    device warp -> rgbd_imagenet_adm_128_large_cond (InpaintCFG, DDIM 3 steps, replace/constrain guidance), batch 2,
+    viewset 'random', guidance 0.5, synthetic weights.  Checks the whole multiview loop runs on the real architectures."""
+    def fw(name, seed, cls):
+        cfg = json.loads(bytes(golden[f"schemacfg_{name}"]).decode())
+        net = backbones.AdmUnet2d(**cfg)
+        net.load_state_dict(unet_ref.make_synthetic_state_dict(cfg, seed=seed))
+        return cls(net.cuda(), timesteps=1000, beta_schedule="linear")
+    fu = fw("rgbd_imagenet_adm_128_large_cfg", 1234, frameworks.ClassifierFreeGuidance)
+    fc = fw("rgbd_imagenet_adm_128_large_cond", 4321, frameworks.InpaintCFG)
+    mvs = build_modelviews("random", 2, rng=np.random.default_rng(3))
+    outs = list(sample_all(fu, fc, [11, 12], 6, 3, mvs, classes=[11, 12], guidance=0.5, batchsize=2, erode_rgb=3))
+    assert len(outs) == 2
+    for meshes, colors, samples, conds in outs:
+        assert samples.shape == (2, 4, 128, 128) and torch.isfinite(samples).all()
+        assert conds["color"].shape == (1, 3, 128, 128) and len(meshes) == 2 and meshes[1].depth.shape == (128, 128, 1)
