@@ -27,8 +27,8 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tiles_n;
   int n_blocks;                // Cout_pad / BN
   int num_tiles;               // tiles_w*tiles_h*tiles_n*n_blocks
-  int seg_chunks[2];           // channels/64 of each K segment (0 = segment unused)
-  int seg_taps[2];             // 9 (3x3) or 1 (1x1)
+  int seg_chunks[3];           // channels/64 of each K segment (0 = segment unused)
+  int seg_taps[3];             // 9 (3x3) or 1 (1x1)
   int Cout;                    // valid output channels
   int ldc;                     // output channel stride (elements) for NHWC modes
   int ldr;                     // residual channel stride (elements)
@@ -37,6 +37,7 @@ struct ConvGemmParams {
   const float* residual;       // fp32 NHWC or nullptr
   void* out;
   double* stats;               // optional [N][Cout][2] per-(sample, channel) sum / sum-of-squares of the output (GroupNorm)
+  int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
@@ -44,6 +45,14 @@ struct ConvGemmParams {
 // kCtas == 2: a CTA pair (cluster of 2, one TPC) computes a 256-pixel x BN tile with tcgen05.mma.cta_group::2 — each CTA
 // stages its own 128 pixels of A and HALF of the weight tile, which cuts the L2 -> shared-memory operand traffic per
 // FLOP by a third and the per-stage footprint to 32 KB (4 stages + the TMA epilogue buffers fit in 227 KB).
+// All TMA descriptors of one launch, passed as a single __grid_constant__ argument.
+struct ConvMaps {
+  CUtensorMap a[3];            // activation segments (fp16 NHWC)
+  CUtensorMap b;               // packed weights
+  CUtensorMap out, res;        // epilogue: output tile store, residual tile load
+  CUtensorMap out16;           // optional fp16 copy of an fp32 output ([32 px][64 ch] boxes)
+};
+
 template <int BN, int kCtas = 1>
 struct ConvGemmCfg {
   static constexpr int BM = 128;
@@ -56,16 +65,17 @@ struct ConvGemmCfg {
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAT_BYTES = 8 * BN * 4;                                // [4 warps][sum|sumsq][BN] fp32
   // per epilogue warp: 2 output staging tiles + 2 residual tiles of [32 pixels][32 channels] fp32 (4 KB each, 128B-swizzled)
-  static constexpr int EPI_BYTES = 4 * 4 * 32 * 32 * 4;
+  // (+ one [32 px][64 ch] fp16 tile for the optional fp16 copy; not available in the single-CTA N=256 configuration)
+  static constexpr bool kHas16 = !(BN == 256 && kCtas == 1);
+  static constexpr int EPI_PER_WARP = (kHas16 ? 5 : 4) * 4096;
+  static constexpr int EPI_BYTES = 4 * EPI_PER_WARP;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
   static constexpr int THREADS = 256;
 };
 
 template <int BN, int kCtas = 1>
 __global__ void __launch_bounds__(256, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                 const __grid_constant__ CUtensorMap mapRes, const ConvGemmParams p) {
+conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, kCtas>;
   constexpr int STAGES = Cfg::STAGES;
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
@@ -85,9 +95,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA0);
-    tma_prefetch_desc(&mapA1);
-    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -115,7 +124,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int w_stride = (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int w_limit = p.num_tiles / kCtas;
 
-  const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1];
+  const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1] + p.seg_chunks[2] * p.seg_taps[2];
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0 && lane == 0) {
@@ -134,8 +143,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int n0 = tn * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
       int kcol = 0;
 #pragma unroll 1
-      for (int seg = 0; seg < 2; ++seg) {
-        const CUtensorMap* mapA = seg == 0 ? &mapA0 : &mapA1;
+      for (int seg = 0; seg < 3; ++seg) {
+        const CUtensorMap* mapA = &maps.a[seg];
         const int taps = p.seg_taps[seg];
         const int chunks = p.seg_chunks[seg];
         if (chunks == 0) continue;
@@ -152,11 +161,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
               const uint32_t bar = full0 + stage * 8;
               tma_load_4d_2sm(mapA, bar, sa, ch * 64, w0 + dx, h0 + dy, n0);
-              tma_load_2d_2sm(&mapB, bar, sb, kcol, nblk * BN + static_cast<int>(cta_rank) * (BN / 2));
+              tma_load_2d_2sm(&maps.b, bar, sb, kcol, nblk * BN + static_cast<int>(cta_rank) * (BN / 2));
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
               tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, w0 + dx, h0 + dy, n0);
-              tma_load_2d(&mapB, &full_bar[stage], sb, kcol, nblk * BN);
+              tma_load_2d(&maps.b, &full_bar[stage], sb, kcol, nblk * BN);
             }
             kcol += 64;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -209,7 +218,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     constexpr int CH = (BN >= 32) ? 32 : 16;
     // ---- TMA epilogue state (CH == 32, fp32 NHWC): the warp's 32 rows form one box (32 ch, TW, box_h, box_n)
     constexpr int NCH = BN / 32;
-    uint8_t* epi_base = stage_smem + quarter * 16384;               // out0 | out1 | res0 | res1, 4 KB each
+    uint8_t* epi_base = stage_smem + quarter * Cfg::EPI_PER_WARP;   // out0 | out1 | res0 | res1 | out16, 4 KB each
     uint64_t* res_bar = res_full + quarter * 2;
     const int box_h0 = (p.TW * p.TH >= 32) ? ((quarter * 32) / p.TW) % p.TH : 0;
     const int box_n0 = (quarter * 32) / (p.TW * p.TH);
@@ -225,7 +234,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
       uint64_t* bar = &res_bar[seq & 1];
       mbar_arrive_expect_tx(bar, 4096);
-      tma_load_4d(&mapRes, bar, epi_base + 8192 + (seq & 1) * 4096, nblk2 * BN + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
+      tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, nblk2 * BN + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
                   tn2 * p.TN + box_n0);
     };
     if constexpr (CH == 32) {
@@ -296,6 +305,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           __syncwarp();
           float4* ob = reinterpret_cast<float4*>(epi_base + (out_cnt & 1) * 4096);
           const float4* rb = reinterpret_cast<const float4*>(epi_base + 8192 + (res_cnt & 1) * 4096);
+          // optional fp16 copy of the same values (operand of the next GroupNorm / skip conv): two 32-column chunks fill one
+          // [32 px][64 ch] tile; its store is committed BEFORE the odd chunk's fp32 store so that wait_group.read<1> at the
+          // top of the next chunk also covers it.
+          uint4* o16 = reinterpret_cast<uint4*>(epi_base + 16384);
+          const bool want16 = Cfg::kHas16 && p.out16;
+          float4 vprev = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int pos = lane * 8 + (j ^ (lane & 7));
@@ -304,11 +319,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             if (tma_res) { const float4 t = rb[pos]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
             if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the batch tail: clipped by TMA, zero for the statistics
             ob[pos] = v;
+            if (want16) {
+              if (j & 1) {
+                uint4 pk;
+                pk.x = pack_h2(vprev.x, vprev.y); pk.y = pack_h2(vprev.z, vprev.w); pk.z = pack_h2(v.x, v.y); pk.w = pack_h2(v.z, v.w);
+                o16[lane * 8 + ((((k & 1) << 2) + (j >> 1)) ^ (lane & 7))] = pk;
+              } else {
+                vprev = v;
+              }
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (!(p.debug & 2)) tma_store_4d(&mapOut, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
+            if constexpr (Cfg::kHas16) {
+              if (p.out16 && (k & 1)) {
+                if (!(p.debug & 2)) tma_store_4d(&maps.out16, epi_base + 16384, col0 - 32, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
+                tma_store_commit();
+              }
+            }
+            if (!(p.debug & 2)) tma_store_4d(&maps.out, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
             tma_store_commit();
             if (tma_res && res_issued < total_seq) issue_res(res_issued);
           }
@@ -381,7 +411,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (!(p.debug & 2)) tma_store_4d(&mapOut, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
+            if (!(p.debug & 2)) tma_store_4d(&maps.out, ob, col0, tw * p.TW, th * p.TH + box_h0, tn * p.TN + box_n0);
             tma_store_commit();
           }
           ++out_cnt;

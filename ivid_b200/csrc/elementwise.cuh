@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 // ----------------------------------------------------------------------------------------------
 struct GnApplyParams {
   const float* x0; const float* x1;     // fp32 NHWC sources (virtual concat along C); x1 may be null (C1 = 0)
-  const __half* x0h;                    // when non-null the (single) source is fp16 NHWC (ResBlock hidden tensor)
+  const __half* x0h; const __half* x1h; // when x0h is non-null the sources are fp16 NHWC (hidden tensor / fp16 copies)
   int C0, C1;
   int N, H, W;                          // INPUT spatial size
   int mode;                             // 0 same, 1 up, 2 down
@@ -96,6 +96,7 @@ struct GnApplyParams {
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
   int pix_per_block;
+  int reverse;                          // 1: blocks walk samples / pixel chunks from the end (see gn_block_pos)
   __half* out_act;                      // fp16 [N][Ho][Wo][C]
   __half* out_raw16;                    // optional fp16 raw copy (same-resolution only) [N][H][W][C]
   float* out_raw32;                     // optional fp32 raw (resampled) [N][Ho][Wo][C]
@@ -103,7 +104,9 @@ struct GnApplyParams {
 
 __device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int w, int c, float (&v)[8]) {
   if (p.x0h != nullptr) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.x0h + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C0 + c));
+    const __half* hs; int hc, hl;
+    if (c < p.C0) { hs = p.x0h; hc = c; hl = p.C0; } else { hs = p.x1h; hc = c - p.C0; hl = p.C1; }
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(hs + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * hl + hc));
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
@@ -117,12 +120,71 @@ __device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int 
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
-  extern __shared__ float s_ab[];        // A then B, each stored [c % 8][c / 8] so a warp's reads are conflict-free
-  __shared__ float s_mean[64], s_rstd[64];
+// Block -> (sample, pixel chunk).  Blocks are dispatched in increasing linear order; with reverse = 1 the first blocks take
+// the LAST samples / pixels.  The producing conv wrote its output in ascending order, so the tail of the tensor is what
+// is still in the 126 MB L2 when this kernel starts; and this kernel then finishes on the head of its output, which is
+// where the consuming conv (ascending) starts reading.
+__device__ __forceinline__ void gn_block_pos(const GnApplyParams& p, int& n, int& bx) {
+  n = p.reverse ? static_cast<int>(gridDim.y - 1 - blockIdx.y) : static_cast<int>(blockIdx.y);
+  bx = p.reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+}
+
+// statistics -> per-channel affine (see above) for sample blockIdx.y, left in shared memory for the whole block
+__device__ __forceinline__ void gn_prologue(const GnApplyParams& p, float* s_ab, float* s_mean, float* s_rstd) {
   const int C = p.C0 + p.C1;
-  const int n = blockIdx.y;
+  int n, bx_unused;
+  gn_block_pos(p, n, bx_unused);
   const int cpg = C / p.groups;
+  if ((cpg & (cpg - 1)) == 0 && cpg <= 32 && C <= 4 * 256 && blockDim.x == 256) {
+    // fast path (power-of-two group width): thread = channel; every global load of the prologue (statistics and affine /
+    // FiLM parameters) is issued up front, the group sums are formed by shuffles, and there is a single barrier
+    constexpr int PF = 4;
+    double2 st[PF];
+    float pg[PF], pb[PF], psc[PF], psh[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < C) {
+        const double* sp = (c < p.C0) ? p.stats0 + (static_cast<size_t>(n) * p.C0 + c) * 2
+                                      : p.stats1 + (static_cast<size_t>(n) * p.C1 + (c - p.C0)) * 2;
+        st[i] = *reinterpret_cast<const double2*>(sp);
+        pg[i] = p.gamma[c];
+        pb[i] = p.beta[c];
+        if (p.film != nullptr) {
+          psc[i] = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c];
+          psh[i] = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + C + c];
+        }
+      }
+    }
+    const double cnt_inv = p.inv_count / cpg;
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < C) {            // C % 32 == 0: whole warps take the branch together
+        double sm = st[i].x, q = st[i].y;
+        for (int off = 1; off < cpg; off <<= 1) {
+          sm += __shfl_xor_sync(0xffffffffu, sm, off);
+          q += __shfl_xor_sync(0xffffffffu, q, off);
+        }
+        const double mean = sm * cnt_inv;
+        double var = q * cnt_inv - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+        const float a0 = rstd * pg[i];
+        const float b0 = pb[i] - static_cast<float>(mean) * a0;
+        float av = a0, bv = b0;
+        if (p.film != nullptr) {
+          const float sc = 1.0f + psc[i];
+          av = a0 * sc;
+          bv = b0 * sc + psh[i];
+        }
+        s_ab[(c & 7) * (C >> 3) + (c >> 3)] = av;
+        s_ab[C + (c & 7) * (C >> 3) + (c >> 3)] = bv;
+      }
+    }
+    __syncthreads();
+    return;
+  }
   for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
     double s = 0.0, q = 0.0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -155,43 +217,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   }
   __syncthreads();
 
+}
+
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float s_ab[];        // A then B, each stored [c % 8][c / 8] so a warp's reads are conflict-free
+  __shared__ float s_mean[64], s_rstd[64];
+  gn_prologue(p, s_ab, s_mean, s_rstd);
+  const int C = p.C0 + p.C1;
+  int n, bx;
+  gn_block_pos(p, n, bx);
   const int c8 = C >> 3;
   const int Ho = p.mode == 1 ? p.H * 2 : (p.mode == 2 ? p.H / 2 : p.H);
   const int Wo = p.mode == 1 ? p.W * 2 : (p.mode == 2 ? p.W / 2 : p.W);
-  const int pix0 = blockIdx.x * p.pix_per_block;
+  const int pix0 = bx * p.pix_per_block;
   const int npix = min(p.pix_per_block, Ho * Wo - pix0);
   const int items = npix * c8;
   int it0 = threadIdx.x;
-  if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
-    // fp16 source (ResBlock hidden tensor): 8 work items per trip kept packed (4 registers each) until consumed, so a
-    // thread still has 128 bytes of reads in flight although each item is only 16 bytes
-    constexpr int U = 8;
-    for (; it0 + (U - 1) * 256 < items; it0 += U * 256) {
-      uint4 raw[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int it = it0 + u * 256;
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(p.x0h + (static_cast<size_t>(n) * Ho * Wo + pix0 + it / c8) * C + (it % c8) * 8));
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int it = it0 + u * 256;
-        const int cg = it % c8;
-        const size_t o = (static_cast<size_t>(n) * Ho * Wo + pix0 + it / c8) * C + cg * 8;
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h2[j]);
-          float y0 = fmaf(f.x, s_ab[(2 * j) * c8 + cg], s_ab[C + (2 * j) * c8 + cg]);
-          float y1 = fmaf(f.y, s_ab[(2 * j + 1) * c8 + cg], s_ab[C + (2 * j + 1) * c8 + cg]);
-          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-          pk[j] = pack_h2(y0, y1);
-        }
-        *reinterpret_cast<uint4*>(p.out_act + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-    }
-  } else if (p.mode == 0) {
+  if (p.mode == 0) {
     // same-resolution fast path (the bulk of the traffic): 4 work items per thread per trip, all 8 x 16-byte loads issued
     // before any is consumed, so a block keeps ~32 KB of reads in flight
     constexpr int U = 4;
@@ -288,6 +330,95 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       stg_f4(p.out_raw32 + o + 4, make_float4(raw[4], raw[5], raw[6], raw[7]));
     }
   }
+}
+
+// Same-resolution GroupNorm apply over fp16 sources (ResBlock hidden tensor, fp16 copies of block outputs, virtual concat
+// of two) with no raw outputs: the bulk of the element-wise traffic of a forward.  8 work items per trip kept packed
+// (4 registers each) until consumed, so a thread has 128 bytes of reads in flight although an item is only 16 bytes.
+// kHoist: the channel-group count divides the block size, so a thread keeps the same 8 channels on every trip and its 16
+// coefficients live in registers (saves 16 shared-memory loads per 16-byte item).
+template <bool kHoist>
+__global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParams p) {
+  extern __shared__ float s_ab[];
+  __shared__ float s_mean[64], s_rstd[64];
+  gn_prologue(p, s_ab, s_mean, s_rstd);
+  const int C = p.C0 + p.C1, c8 = C >> 3, c80 = p.C0 >> 3;
+  int n, bx;
+  gn_block_pos(p, n, bx);
+  const int HW = p.H * p.W;
+  const int pix0 = bx * p.pix_per_block;
+  const int npix = min(p.pix_per_block, HW - pix0);
+  const int items = npix * c8;
+  constexpr int U = 8;
+  float A[8], B[8];
+  if (kHoist) {
+    const int cg = threadIdx.x % c8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { A[j] = s_ab[j * c8 + cg]; B[j] = s_ab[C + j * c8 + cg]; }
+  }
+  auto apply8 = [&](const uint4& rawv, int cg, __half* dst) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&rawv);
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      float y0, y1;
+      if (kHoist) {
+        y0 = fmaf(f.x, A[2 * j], B[2 * j]);
+        y1 = fmaf(f.y, A[2 * j + 1], B[2 * j + 1]);
+      } else {
+        y0 = fmaf(f.x, s_ab[(2 * j) * c8 + cg], s_ab[C + (2 * j) * c8 + cg]);
+        y1 = fmaf(f.y, s_ab[(2 * j + 1) * c8 + cg], s_ab[C + (2 * j + 1) * c8 + cg]);
+      }
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      pk[j] = pack_h2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  if (kHoist) {
+    // division-free addressing: the thread owns channel group cg and every (256 / c8)-th pixel starting at pr
+    const int cg = threadIdx.x % c8, pr = threadIdx.x / c8, ppt = 256 / c8;
+    const size_t px0 = static_cast<size_t>(n) * HW + pix0 + pr;
+    const __half* src;
+    size_t sstep;
+    if (cg < c80) { src = p.x0h + px0 * p.C0 + cg * 8; sstep = static_cast<size_t>(ppt) * p.C0; }
+    else { src = p.x1h + px0 * p.C1 + (cg - c80) * 8; sstep = static_cast<size_t>(ppt) * p.C1; }
+    __half* dst = p.out_act + px0 * C + cg * 8;
+    const size_t dstep = static_cast<size_t>(ppt) * C;
+    int left = pr < npix ? (npix - pr + ppt - 1) / ppt : 0;      // pixels of this thread
+    for (; left >= U; left -= U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src + u * sstep));
+#pragma unroll
+      for (int u = 0; u < U; ++u) apply8(raw[u], cg, dst + u * dstep);
+      src += U * sstep;
+      dst += U * dstep;
+    }
+    for (; left > 0; --left) {
+      apply8(__ldg(reinterpret_cast<const uint4*>(src)), cg, dst);
+      src += sstep;
+      dst += dstep;
+    }
+    return;
+  }
+  auto src_of = [&](int it) {
+    const int cg = it % c8;
+    const size_t px = static_cast<size_t>(n) * HW + pix0 + it / c8;
+    return cg < c80 ? p.x0h + px * p.C0 + cg * 8 : p.x1h + px * p.C1 + (cg - c80) * 8;
+  };
+  auto finish = [&](int it, const uint4& rawv) {
+    apply8(rawv, it % c8, p.out_act + (static_cast<size_t>(n) * HW + pix0 + it / c8) * C + (it % c8) * 8);
+  };
+  int it0 = threadIdx.x;
+  for (; it0 + (U - 1) * 256 < items; it0 += U * 256) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(src_of(it0 + u * 256)));
+#pragma unroll
+    for (int u = 0; u < U; ++u) finish(it0 + u * 256, raw[u]);
+  }
+  for (int it = it0; it < items; it += 256) finish(it, __ldg(reinterpret_cast<const uint4*>(src_of(it))));
 }
 
 // ----------------------------------------------------------------------------------------------

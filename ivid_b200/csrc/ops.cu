@@ -16,7 +16,7 @@ namespace ivid {
 // conv implicit GEMM
 // --------------------------------------------------------------------------------------------------
 struct ConvLaunch {
-  CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;
+  ConvMaps maps;
   ConvGemmParams p;
   int BN;
   int grid;
@@ -59,11 +59,18 @@ static void set_conv_attr() {
   });
 }
 
+bool conv_can_out16(int cout) {
+  static const int dbg = [] { const char* e = getenv("IVID_CONV_DEBUG"); return e ? atoi(e) : 0; }();
+  static const bool off = getenv("IVID_NO_OUT16") != nullptr;
+  return cout % 64 == 0 && !(dbg & 16) && !off;
+}
+
 ConvLaunch* conv_launch_create(const ConvDesc& d) {
   IVID_REQUIRE(d.C0 > 0 && d.C0 % 64 == 0, "conv: segment-0 channels must be a positive multiple of 64");
   IVID_REQUIRE(d.C1 % 64 == 0, "conv: segment-1 channels must be a multiple of 64");
   IVID_REQUIRE(d.taps0 == 9 || d.taps0 == 1, "conv: only 3x3 (pad 1) and 1x1 kernels are on this path");
   IVID_REQUIRE(d.taps1 == 9 || d.taps1 == 1, "conv: only 3x3 (pad 1) and 1x1 kernels are on this path");
+  IVID_REQUIRE(d.C2 % 64 == 0 && (d.taps2 == 9 || d.taps2 == 1), "conv: segment 2 must be a multiple of 64 channels, 3x3 or 1x1");
   auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   IVID_REQUIRE(is_pow2(d.H) && is_pow2(d.W), "conv: spatial size must be a power of two");
   auto* l = new ConvLaunch();
@@ -76,10 +83,19 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   p.tiles_h = d.H / p.TH;
   p.tiles_n = (d.N + p.TN - 1) / p.TN;
   l->BN = conv_pick_bn(d.cout_pad, p.tiles_w * p.tiles_h * p.tiles_n);
+  {
+    // N = 256 tiles run as CTA pairs; when the layer cannot be paired (odd number of pixel tiles) the 128-wide
+    // single-CTA configuration is used instead (it has the shared memory for every epilogue feature)
+    static const bool pair_ok = getenv("IVID_NO_2CTA") == nullptr;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    l->ctas = (pair_ok && l->BN == 256 && m_tiles % 2 == 0 && m_tiles >= 2) ? 2 : 1;
+    if (l->BN == 256 && l->ctas == 1 && (pair_ok || d.out16 != nullptr)) l->BN = 128;
+  }
   p.n_blocks = d.cout_pad / l->BN;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
   p.seg_chunks[0] = d.C0 / 64; p.seg_taps[0] = d.taps0;
   p.seg_chunks[1] = d.C1 / 64; p.seg_taps[1] = d.C1 > 0 ? d.taps1 : 0;
+  p.seg_chunks[2] = d.C2 / 64; p.seg_taps[2] = d.C2 > 0 ? d.taps2 : 0;
   p.Cout = d.cout; p.ldc = d.ldc; p.ldr = d.ldr; p.out_mode = d.out_mode;
   p.bias = d.bias; p.residual = d.residual; p.out = d.out;
   {
@@ -90,18 +106,15 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   p.stats = (d.stats != nullptr && conv_can_fuse_stats(d.H, d.W) && d.out_mode != 2) ? d.stats : nullptr;
   IVID_REQUIRE(d.stats == nullptr || p.stats != nullptr, "conv: fused statistics need >= 32 pixels per sample per warp");
   IVID_REQUIRE(d.out_mode == 2 || (d.cout % 8 == 0 && d.ldc % 8 == 0), "conv: NHWC output needs Cout % 8 == 0");
-  const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0);
-  l->mapA0 = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
-  l->mapA1 = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : l->mapA0;
-  // CTA pairs for the wide tiles: needs an even number of pixel tiles (the pair splits two adjacent ones)
-  {
-    static const bool pair_ok = getenv("IVID_NO_2CTA") == nullptr;
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    l->ctas = (pair_ok && l->BN == 256 && m_tiles % 2 == 0 && m_tiles >= 2) ? 2 : 1;
-  }
-  l->mapB = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / l->ctas);
+  const int Ktot = d.taps0 * d.C0 + (d.C1 > 0 ? d.taps1 * d.C1 : 0) + (d.C2 > 0 ? d.taps2 * d.C2 : 0);
+  ConvMaps& M = l->maps;
+  M.a[0] = make_act_map(d.act0, d.N, d.H, d.W, d.C0, p.TW, p.TH, p.TN);
+  M.a[1] = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : M.a[0];
+  M.a[2] = d.C2 > 0 ? make_act_map(d.act2, d.N, d.H, d.W, d.C2, p.TW, p.TH, p.TN) : M.a[0];
+  M.b = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / l->ctas);
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
-  l->mapOut = l->mapA0; l->mapRes = l->mapA0;
+  M.out = M.a[0]; M.res = M.a[0]; M.out16 = M.a[0];
+  p.out16 = 0;
   p.epi_tma = 0;
   if (d.out_mode == 0 && l->BN >= 32 && d.cout % 32 == 0 && !(p.debug & 16)) {
     const int bh = std::min(p.TH, 32 / p.TW), bn = 32 / (p.TW * bh);
@@ -111,15 +124,23 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
       const uint32_t box[4] = {32, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
       return make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     };
-    l->mapOut = f32_map(d.out, d.ldc);
-    if (d.residual != nullptr) l->mapRes = f32_map(d.residual, d.ldr);
+    M.out = f32_map(d.out, d.ldc);
+    if (d.residual != nullptr) M.res = f32_map(d.residual, d.ldr);
     p.epi_tma = 1;
+    if (d.out16 != nullptr) {
+      IVID_REQUIRE(d.cout % 64 == 0 && !(l->BN == 256 && l->ctas == 1), "conv: fp16 output copy needs Cout % 64 == 0");
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.ldc), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.N)};
+      const uint64_t str[3] = {static_cast<uint64_t>(d.ldc) * 2, static_cast<uint64_t>(d.W) * d.ldc * 2, static_cast<uint64_t>(d.H) * d.W * d.ldc * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+      M.out16 = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out16, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      p.out16 = 1;
+    }
   } else if (d.out_mode == 1 && l->BN >= 64 && d.cout % 64 == 0 && d.residual == nullptr && !(p.debug & 16)) {
     const int bh = std::min(p.TH, 32 / p.TW), bn = 32 / (p.TW * bh);
     const uint64_t dims[4] = {static_cast<uint64_t>(d.ldc), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.N)};
     const uint64_t str[3] = {static_cast<uint64_t>(d.ldc) * 2, static_cast<uint64_t>(d.W) * d.ldc * 2, static_cast<uint64_t>(d.H) * d.W * d.ldc * 2};
     const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
-    l->mapOut = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    M.out = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     p.epi_tma = 2;
   }
   // fused statistics are produced by the TMA epilogues only
@@ -133,8 +154,7 @@ int conv_launch_bn(const ConvLaunch* l) { return l->BN; }
 template <int BN>
 static void run_conv(const ConvLaunch* l, cudaStream_t s) {
   set_conv_attr<BN>();
-  conv_gemm_kernel<BN, 1><<<l->grid, ConvGemmCfg<BN, 1>::THREADS, ConvGemmCfg<BN, 1>::SMEM_BYTES, s>>>(l->mapA0, l->mapA1, l->mapB,
-                                                                                                      l->mapOut, l->mapRes, l->p);
+  conv_gemm_kernel<BN, 1><<<l->grid, ConvGemmCfg<BN, 1>::THREADS, ConvGemmCfg<BN, 1>::SMEM_BYTES, s>>>(l->maps, l->p);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
@@ -153,7 +173,7 @@ static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->mapA0, l->mapA1, l->mapB, l->mapOut, l->mapRes, l->p));
+  IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->maps, l->p));
 }
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {
   ConvLaunch tmp = *l;
@@ -230,9 +250,9 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   IVID_REQUIRE(d.groups >= 1 && d.groups <= 64 && C % d.groups == 0, "group norm: groups must divide channels (<= 64 groups)");
   IVID_REQUIRE(d.stats0 != nullptr && d.gamma != nullptr && d.beta != nullptr, "gn_apply: statistics / affine parameters missing");
   GnApplyParams p;
-  p.x0 = d.x0; p.x1 = d.x1; p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
+  p.x0 = static_cast<const float*>(d.x0); p.x1 = static_cast<const float*>(d.x1); p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
   p.x0h = d.x0_half ? reinterpret_cast<const __half*>(d.x0) : nullptr;
-  IVID_REQUIRE(!d.x0_half || d.C1 == 0, "gn_apply: fp16 source cannot be part of a concat");
+  p.x1h = d.x0_half ? reinterpret_cast<const __half*>(d.x1) : nullptr;
   p.silu = d.silu;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
@@ -249,9 +269,18 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     const int small = std::max(1, 1024 / (C / 8));      // at least ~4 work items per thread
     p.pix_per_block = std::max(1, std::min(Ho * Wo, mode == 0 ? small : (mode == 2 ? std::max(by_wave / 4, small) : std::max(by_wave, small))));
   }
+  {
+    static const bool fwd = getenv("IVID_GN_FWD") != nullptr;
+    p.reverse = fwd ? 0 : 1;
+  }
   dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;
-  gn_apply_kernel<<<grid, 256, smem, s>>>(p);
+  if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
+    if (256 % (C / 8) == 0) gn_apply_h16_kernel<true><<<grid, 256, smem, s>>>(p);
+    else gn_apply_h16_kernel<false><<<grid, 256, smem, s>>>(p);
+  } else {
+    gn_apply_kernel<<<grid, 256, smem, s>>>(p);
+  }
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -267,8 +296,47 @@ void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 
+void launch_film_table(const float* emb, const float* Wp, const float* bias, float* x_t, float* out, int N, int K, int O, cudaStream_t s) {
+  IVID_REQUIRE(K % 32 == 0 && O % 4 == 0, "film table: K % 32 == 0");
+  static std::once_flag once;
+  std::call_once(once, [] {
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(film_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FilmCfg::SMEM_BYTES));
+  });
+  const int nblk = (N + 31) / 32;
+  silu_transpose_kernel<<<std::min(256, (nblk * K * 32 + 255) / 256), 256, 0, s>>>(emb, x_t, N, K, 1);
+  const int tiles = (O + FilmCfg::TO - 1) / FilmCfg::TO;
+  dim3 grid(std::min(tiles, std::max(1, sm_count() / nblk)), nblk);
+  film_table_kernel<<<grid, FilmCfg::THREADS, FilmCfg::SMEM_BYTES, s>>>(Wp, x_t, bias, out, N, K, O);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
 void launch_linear(const float* in, const float* W, const float* bias, float* out, int N, int K, int O, int silu_in,
                    const float* label_emb, const int64_t* classes, int Ncls, cudaStream_t s) {
+  if ((K == 256 || K == 512 || K == 1024) && O <= 8192) {
+    dim3 grid((O + 7) / 8, (N + 31) / 32);
+    const size_t smem = static_cast<size_t>(32) * K * 4;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      IVID_CHECK_CUDA(cudaFuncSetAttribute(linear_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 256 * 4));
+      IVID_CHECK_CUDA(cudaFuncSetAttribute(linear_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 512 * 4));
+      IVID_CHECK_CUDA(cudaFuncSetAttribute(linear_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));
+    });
+    auto go = [&](auto kern) { kern<<<grid, 256, smem, s>>>(in, W, bias, out, N, O, silu_in, label_emb, classes, Ncls); };
+    if (K == 256) go(linear_warp_kernel<2>); else if (K == 512) go(linear_warp_kernel<4>); else go(linear_warp_kernel<8>);
+    IVID_CHECK_CUDA(cudaGetLastError());
+    return;
+  }
+  if (K % 32 == 0) {
+    if (O >= 128 * 64) {
+      dim3 grid((O + 127) / 128, (N + 31) / 32);
+      linear_tiled_kernel<4><<<grid, 256, 0, s>>>(in, W, bias, out, N, K, O, silu_in, label_emb, classes, Ncls);
+    } else {
+      dim3 grid((O + 63) / 64, (N + 31) / 32);
+      linear_tiled_kernel<2><<<grid, 256, 0, s>>>(in, W, bias, out, N, K, O, silu_in, label_emb, classes, Ncls);
+    }
+    IVID_CHECK_CUDA(cudaGetLastError());
+    return;
+  }
   dim3 grid((O + 63) / 64, (N + 31) / 32);
   linear_rows_kernel<<<grid, 256, 0, s>>>(in, W, bias, out, N, K, O, silu_in, label_emb, classes, Ncls);
   IVID_CHECK_CUDA(cudaGetLastError());

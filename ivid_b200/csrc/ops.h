@@ -16,6 +16,8 @@ struct AttnLaunch;
 struct ConvDesc {
   const void* act0 = nullptr; int C0 = 0; int taps0 = 9;   // segment 0: fp16 NHWC activation, 9 = 3x3, 1 = 1x1
   const void* act1 = nullptr; int C1 = 0; int taps1 = 1;   // optional segment 1 (1x1 skip over another tensor)
+  const void* act2 = nullptr; int C2 = 0; int taps2 = 1;   // optional segment 2 (second half of a virtual concat)
+  void* out16 = nullptr;                                   // optional fp16 NHWC copy of an fp32 output (same ldc)
   const void* weight = nullptr;                            // fp16 [cout_pad][Ktot], Ktot = taps0*C0 + taps1*C1
   int cout_pad = 0;
   int cout = 0;                                            // valid output channels
@@ -33,6 +35,8 @@ void conv_launch_run(const ConvLaunch* l, cudaStream_t s);
 int conv_launch_bn(const ConvLaunch* l);
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s);   // same launch, output pointer overridden
 int conv_pick_bn(int cout_pad, int m_tiles = 0);          // m_tiles > 0: wave-quantisation aware choice
+// whether a conv with this many (unpadded) output channels can also emit the fp16 copy of its fp32 NHWC output
+bool conv_can_out16(int cout);
 bool conv_can_fuse_stats(int H, int W);                    // epilogue statistics need >= 32 pixels of one sample per warp
 int conv_pad_cout(int cout);
 
@@ -42,8 +46,8 @@ void attn_launch_run(const AttnLaunch* l, cudaStream_t s);
 
 void launch_gn_stats(const float* x, double* stats, int N, int HW, int C, cudaStream_t s);
 struct GnApplyDesc {
-  const float* x0 = nullptr; const float* x1 = nullptr; int C0 = 0, C1 = 0;
-  bool x0_half = false;                                            // x0 points at fp16 data (C1 must be 0)
+  const void* x0 = nullptr; const void* x1 = nullptr; int C0 = 0, C1 = 0;
+  bool x0_half = false;                                            // sources point at fp16 data (both, when concatenated)
   int N = 0, H = 0, W = 0; int mode = 0; int silu = 1;
   const double* stats0 = nullptr; const double* stats1 = nullptr;   // per-(sample, channel) sum / sumsq of each source
   int groups = 32; float eps = 1e-5f;
@@ -62,6 +66,9 @@ struct CondPackDesc {
 void launch_cond_pack(const CondPackDesc& d, cudaStream_t s);   // sampler.cu
 
 void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float* out, int N, cudaStream_t s);
+// FiLM table (all ResBlock emb_layers as one product): out = silu(emb) * Wp^T + bias, Wp in the swizzled K-chunk-major
+// layout described at film_table_kernel; x_t is a [ceil(N/32)][K][32] fp32 scratch.
+void launch_film_table(const float* emb, const float* Wp, const float* bias, float* x_t, float* out, int N, int K, int O, cudaStream_t s);
 void launch_linear(const float* in, const float* W, const float* bias, float* out, int N, int K, int O, int silu_in,
                    const float* label_emb, const int64_t* classes, int Ncls, cudaStream_t s);
 

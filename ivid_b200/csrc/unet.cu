@@ -309,7 +309,18 @@ void Unet::finalize(int device) {
     for (const auto& r : res_) {
       const auto& w = P(r.pfx + ".emb_layers.1.weight").host;
       const auto& b = P(r.pfx + ".emb_layers.1.bias").host;
-      std::memcpy(ab.at<float>(film_.w_off) + static_cast<size_t>(r.film_off) * embed_dim_, w.data(), w.size() * 4);
+      // swizzled K-chunk-major [E/32][film_total][32] when E % 32 == 0 (see film_table_kernel), row-major otherwise
+      if (embed_dim_ % 32 == 0) {
+        float* dst = ab.at<float>(film_.w_off);
+        const int rows_w = static_cast<int>(w.size() / embed_dim_);
+        for (int o = 0; o < rows_w; ++o)
+          for (int kc = 0; kc < embed_dim_; kc += 32)
+            for (int g = 0; g < 8; ++g)      // 16-byte groups XOR-swizzled with the output index (film_table_kernel)
+              std::memcpy(dst + (static_cast<size_t>(kc / 32) * film_total_ + r.film_off + o) * 32 + ((g ^ ((r.film_off + o) & 7)) << 2),
+                          w.data() + static_cast<size_t>(o) * embed_dim_ + kc + g * 4, 16);
+      } else {
+        std::memcpy(ab.at<float>(film_.w_off) + static_cast<size_t>(r.film_off) * embed_dim_, w.data(), w.size() * 4);
+      }
       std::memcpy(ab.at<float>(film_.b_off) + r.film_off, b.data(), b.size() * 4);
     }
   }
@@ -382,6 +393,7 @@ struct Plan {
 namespace {
 struct Act {          // fp32 NHWC residual-stream tensor with per-(n,channel) statistics
   float* data = nullptr;
+  __half* d16 = nullptr;    // fp16 copy written by the producing conv (operand of the next GroupNorm / 1x1 skip conv)
   double* stats = nullptr;
   int C = 0, H = 0, W = 0;
 };
@@ -474,6 +486,7 @@ Plan* Unet::build_plan(int N) {
     auto new_act = [&](int C, int H, int Wd) {
       Act a; a.C = C; a.H = H; a.W = Wd;
       a.data = static_cast<float*>(bump.take(static_cast<size_t>(N) * H * Wd * C * 4));
+      if (conv_can_out16(C)) a.d16 = static_cast<__half*>(bump.take(static_cast<size_t>(N) * H * Wd * C * 2));
       a.stats = take_stats(C);
       return a;
     };
@@ -491,6 +504,7 @@ Plan* Unet::build_plan(int N) {
     float* s_e1 = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
     float* s_emb = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
     float* s_film = static_cast<float*>(bump.take(static_cast<size_t>(N) * film_total_ * 4));
+    float* s_xt = static_cast<float*>(bump.take(static_cast<size_t>((N + 31) / 32) * embed_dim_ * 32 * 4));
 
     Act pending_stats; bool has_pending_stats = false;
     auto add_conv = [&](ConvDesc d, const Act* stats_of = nullptr) {
@@ -502,15 +516,16 @@ Plan* Unet::build_plan(int N) {
       if (!create) return;
       ConvLaunch* l = conv_launch_create(d);
       pl->convs.push_back(l);
-      const double K = static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0);
+      const double K = static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0) +
+                       (d.C2 > 0 ? static_cast<double>(d.taps2) * d.C2 : 0.0);
       const double M = static_cast<double>(d.N) * d.H * d.W;
       static const char* names[] = {"conv_gemm<16>", "conv_gemm<64>", "conv_gemm<128>", "conv_gemm<256>"};
       const int bn = conv_launch_bn(l);
       pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * d.cout,
-                  M * K / (d.taps0 == 9 ? 9.0 : 1.0) * 2 + M * d.cout * (d.out_mode == 1 ? 2 : 4) + K * d.cout_pad * 2,
-                  std::to_string(d.H) + "x" + std::to_string(d.W) + " " + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") +
+                  M * (d.C0 + d.C1 + d.C2) * 2 + M * d.cout * ((d.out_mode == 1 ? 2 : 4) + (d.out16 ? 2 : 0) + (d.residual ? 4 : 0)) + K * d.cout_pad * 2,
+                  std::to_string(d.H) + "x" + std::to_string(d.W) + " " + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") + (d.C2 ? "+" + std::to_string(d.C2) : "") +
                       "->" + std::to_string(d.cout) + " k" + std::to_string(d.taps0) + (d.residual ? " res" : "") + (d.stats ? " stats" : "") +
-                      (d.out_mode == 1 ? " f16" : ""));
+                      (d.out_mode == 1 ? " f16" : "") + (d.out16 ? " +f16" : ""));
       pl->ops.push_back([l](cudaStream_t s) { conv_launch_run(l, s); });
     };
     auto add_stats = [&](const Act& a) {
@@ -555,12 +570,16 @@ Plan* Unet::build_plan(int N) {
       const float* lab = cfg_.num_classes > 0 ? Wf(label_off_) : nullptr;
       const float *wf = Wf(film_.w_off), *bf = Wf(film_.b_off);
       const int FT = film_total_;
-      pl->ops.tag("embed", 2.0 * N * E * (mc + E + FT), 4.0 * E * (mc + E + FT));
+      pl->ops.tag("embed", 2.0 * N * E * (mc + E), 4.0 * E * (mc + E), "posenc+time_embed");
       pl->ops.push_back([=](cudaStream_t s) {
         launch_posenc(pl->t, N, freqs, half, s_pe, N, s);
         launch_linear(s_pe, w1, b1, s_e1, N, mc, E, 0, nullptr, nullptr, 1, s);
         launch_linear(s_e1, w2, b2, s_emb, N, E, E, 1, pl->classes ? lab : nullptr, pl->classes, N, s);
-        launch_linear(s_emb, wf, bf, s_film, N, E, FT, 1, nullptr, nullptr, 1, s);
+      });
+      pl->ops.tag("embed", 2.0 * N * E * FT, 4.0 * E * FT, "film table O=" + std::to_string(FT));
+      pl->ops.push_back([=](cudaStream_t s) {
+        if (E % 32 == 0) launch_film_table(s_emb, wf, bf, s_xt, s_film, N, E, FT, s);
+        else launch_linear(s_emb, wf, bf, s_film, N, E, FT, 1, nullptr, nullptr, 1, s);
       });
     }
 
@@ -585,7 +604,7 @@ Plan* Unet::build_plan(int N) {
       ConvDesc d;
       d.act0 = s_in; d.C0 = 64; d.taps0 = 9;
       d.weight = W8(in_conv_.w_off); d.cout_pad = in_conv_.cout_pad; d.cout = in_conv_.cout; d.bias = Wf(in_conv_.b_off);
-      d.out = cur.data; d.ldc = cur.C; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
+      d.out = cur.data; d.out16 = cur.d16; d.ldc = cur.C; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
       add_conv(d, &cur);
       add_stats(cur);
     }
@@ -603,9 +622,14 @@ Plan* Unet::build_plan(int N) {
       // GN1 + SiLU (+ resample) -> a1 ; raw fp16 copy for the 1x1 skip conv ; raw fp32 for resampled identity skip
       add_coeff(x0, x1, r.gn1, -1);
       GnApplyDesc g1;
-      g1.x0 = x0.data; g1.x1 = x1 ? x1->data : nullptr; g1.C0 = x0.C; g1.C1 = x1 ? x1->C : 0;
+      // same-resolution blocks read the fp16 copies their producers wrote (half the GroupNorm read traffic, and the 1x1 skip
+      // conv takes them directly as K segments: no raw copy pass)
+      const bool use16 = r.mode == 0 && !need_xr && x0.d16 != nullptr && (x1 == nullptr || x1->d16 != nullptr);
+      if (use16) { g1.x0 = x0.d16; g1.x1 = x1 ? x1->d16 : nullptr; g1.x0_half = true; }
+      else { g1.x0 = x0.data; g1.x1 = x1 ? x1->data : nullptr; }
+      g1.C0 = x0.C; g1.C1 = x1 ? x1->C : 0;
       g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1;
-      g1.out_act = s_a1; g1.out_raw16 = r.skip_conv ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
+      g1.out_act = s_a1; g1.out_raw16 = (r.skip_conv && !use16) ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
       IVID_REQUIRE(!(r.skip_conv && r.mode != 0), "internal: up/down ResBlocks keep the channel count");
       add_apply(g1);
       // conv1 -> h (fp32) ; stats
@@ -634,10 +658,13 @@ Plan* Unet::build_plan(int N) {
       {
         ConvDesc d;
         d.act0 = s_a2; d.C0 = r.cout; d.taps0 = 9;
-        if (r.skip_conv) { d.act1 = s_xh; d.C1 = r.cin; d.taps1 = 1; }
+        if (r.skip_conv && use16) {
+          d.act1 = x0.d16; d.C1 = x0.C; d.taps1 = 1;
+          if (x1 != nullptr) { d.act2 = x1->d16; d.C2 = x1->C; d.taps2 = 1; }
+        } else if (r.skip_conv) { d.act1 = s_xh; d.C1 = r.cin; d.taps1 = 1; }
         d.weight = W8(r.conv2.w_off); d.cout_pad = r.conv2.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv2.b_off);
         if (identity) { d.residual = need_xr ? s_xr : x0.data; d.ldr = r.cout; }
-        d.out = out.data; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
+        d.out = out.data; d.out16 = out.d16; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
         add_conv(d, &out);
         add_stats(out);
       }
@@ -648,7 +675,8 @@ Plan* Unet::build_plan(int N) {
       const int T = x.H * x.W;
       add_coeff(x, nullptr, a.gn, -1);
       GnApplyDesc g;
-      g.x0 = x.data; g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.out_act = s_a1;
+      if (x.d16 != nullptr) { g.x0 = x.d16; g.x0_half = true; } else g.x0 = x.data;
+      g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.out_act = s_a1;
       add_apply(g);
       {
         ConvDesc d;
@@ -669,7 +697,7 @@ Plan* Unet::build_plan(int N) {
         d.act0 = s_a2; d.C0 = a.C; d.taps0 = 1;
         d.weight = W8(a.proj.w_off); d.cout_pad = a.proj.cout_pad; d.cout = a.C; d.bias = Wf(a.proj.b_off);
         d.residual = x.data; d.ldr = a.C;
-        d.out = out.data; d.ldc = a.C; d.out_mode = 0; d.N = N; d.H = x.H; d.W = x.W;
+        d.out = out.data; d.out16 = out.d16; d.ldc = a.C; d.out_mode = 0; d.N = N; d.H = x.H; d.W = x.W;
         add_conv(d, &out);
         add_stats(out);
       }
@@ -700,7 +728,8 @@ Plan* Unet::build_plan(int N) {
     // ---- output head: GN + SiLU + conv3x3 -> eps (fp32 NCHW) ----
     add_coeff(cur, nullptr, out_gn_, -1);
     GnApplyDesc go;
-    go.x0 = cur.data; go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.out_act = s_a1;
+    if (cur.d16 != nullptr) { go.x0 = cur.d16; go.x0_half = true; } else go.x0 = cur.data;
+    go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.out_act = s_a1;
     add_apply(go);
     if (create) {
       ConvDesc d;
