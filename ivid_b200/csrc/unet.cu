@@ -395,6 +395,7 @@ struct Act {          // fp32 NHWC residual-stream tensor with per-(n,channel) s
   float* data = nullptr;
   __half* d16 = nullptr;    // fp16 copy written by the producing conv (operand of the next GroupNorm / 1x1 skip conv)
   double* stats = nullptr;
+  int id = -1;              // position in creation order (fp32 liveness table of build_plan)
   int C = 0, H = 0, W = 0;
 };
 struct Bump {
@@ -455,9 +456,13 @@ Plan* Unet::build_plan(int N) {
     max_act16 = std::max(max_act16, static_cast<size_t>(N) * S * S * std::max(64, final_ch_));
   }
 
-  // The same allocation sequence is run twice: once to size the workspace, once to build the launches.
+  // The same allocation sequence is run three times: once to find out which block outputs are ever read in fp32 (residual
+  // adds, resampling blocks; everything else consumes the fp16 copy), once to size the workspace, once to build the launches.
+  std::vector<char> need32;
+  bool collect = true;
   auto layout = [&](uint8_t* base, bool create) -> size_t {
     Bump bump(base);
+    int next_id = 0;
     // statistics arena is placed first so that its base is known while creating ops
     // (sized generously: every tensor needs N*C*16 bytes; bound by total params walk below)
     size_t stats_cap = 0;
@@ -485,7 +490,8 @@ Plan* Unet::build_plan(int N) {
     auto stats_ptr = [&](const Act& a) { return a.stats; };
     auto new_act = [&](int C, int H, int Wd) {
       Act a; a.C = C; a.H = H; a.W = Wd;
-      a.data = static_cast<float*>(bump.take(static_cast<size_t>(N) * H * Wd * C * 4));
+      a.id = next_id++;
+      if (collect) need32.resize(a.id + 1, 0);
       if (conv_can_out16(C)) a.d16 = static_cast<__half*>(bump.take(static_cast<size_t>(N) * H * Wd * C * 2));
       a.stats = take_stats(C);
       return a;
@@ -506,6 +512,17 @@ Plan* Unet::build_plan(int N) {
     float* s_film = static_cast<float*>(bump.take(static_cast<size_t>(N) * film_total_ * 4));
     float* s_xt = static_cast<float*>(bump.take(static_cast<size_t>((N + 31) / 32) * embed_dim_ * 32 * 4));
 
+    // fp32 storage of a block output is allocated by its producer, and only when some consumer reads it (or the fp16-only
+    // epilogue is not available: no fp16 copy, residual add, statistics not fusable)
+    auto alloc32 = [&](Act& a) { a.data = static_cast<float*>(bump.take(static_cast<size_t>(N) * a.H * a.W * a.C * 4)); };
+    auto only16 = [&](const Act& a, bool has_residual) {
+      return !collect && !need32[a.id] && a.d16 != nullptr && !has_residual && conv_can_fuse_stats(a.H, a.W);
+    };
+    auto use32 = [&](const Act& a) -> const float* {
+      if (collect) need32[a.id] = 1;
+      else if (create) IVID_REQUIRE(a.data != nullptr, "internal: fp32 tensor was not materialised");
+      return a.data;
+    };
     Act pending_stats; bool has_pending_stats = false;
     auto add_conv = [&](ConvDesc d, const Act* stats_of = nullptr) {
       // GroupNorm statistics of the output are accumulated in the conv epilogue whenever the tile geometry allows
@@ -532,6 +549,7 @@ Plan* Unet::build_plan(int N) {
       if (!create || !has_pending_stats) return;      // already fused into the producing conv
       has_pending_stats = false;
       const float* x = a.data; double* st = stats_ptr(a);
+      IVID_REQUIRE(!create || x != nullptr, "internal: statistics pass over a tensor without fp32 storage");
       const int HW = a.H * a.W, C = a.C;
       pl->ops.tag("gn_stats", 0, static_cast<double>(N) * HW * C * 4);
       pl->ops.push_back([=](cudaStream_t s) { launch_gn_stats(x, st, N, HW, C, s); });
@@ -604,7 +622,9 @@ Plan* Unet::build_plan(int N) {
       ConvDesc d;
       d.act0 = s_in; d.C0 = 64; d.taps0 = 9;
       d.weight = W8(in_conv_.w_off); d.cout_pad = in_conv_.cout_pad; d.cout = in_conv_.cout; d.bias = Wf(in_conv_.b_off);
-      d.out = cur.data; d.out16 = cur.d16; d.ldc = cur.C; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
+      if (only16(cur, false)) { d.out = cur.d16; d.out_mode = 1; }
+      else { alloc32(cur); d.out = cur.data; d.out16 = cur.d16; d.out_mode = 0; }
+      d.ldc = cur.C; d.N = N; d.H = S; d.W = S;
       add_conv(d, &cur);
       add_stats(cur);
     }
@@ -626,7 +646,7 @@ Plan* Unet::build_plan(int N) {
       // conv takes them directly as K segments: no raw copy pass)
       const bool use16 = r.mode == 0 && !need_xr && x0.d16 != nullptr && (x1 == nullptr || x1->d16 != nullptr);
       if (use16) { g1.x0 = x0.d16; g1.x1 = x1 ? x1->d16 : nullptr; g1.x0_half = true; }
-      else { g1.x0 = x0.data; g1.x1 = x1 ? x1->data : nullptr; }
+      else { g1.x0 = use32(x0); g1.x1 = x1 ? use32(*x1) : nullptr; }
       g1.C0 = x0.C; g1.C1 = x1 ? x1->C : 0;
       g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1;
       g1.out_act = s_a1; g1.out_raw16 = (r.skip_conv && !use16) ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
@@ -663,8 +683,10 @@ Plan* Unet::build_plan(int N) {
           if (x1 != nullptr) { d.act2 = x1->d16; d.C2 = x1->C; d.taps2 = 1; }
         } else if (r.skip_conv) { d.act1 = s_xh; d.C1 = r.cin; d.taps1 = 1; }
         d.weight = W8(r.conv2.w_off); d.cout_pad = r.conv2.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv2.b_off);
-        if (identity) { d.residual = need_xr ? s_xr : x0.data; d.ldr = r.cout; }
-        d.out = out.data; d.out16 = out.d16; d.ldc = r.cout; d.out_mode = 0; d.N = N; d.H = Ho; d.W = Wo;
+        if (identity) { d.residual = need_xr ? s_xr : use32(x0); d.ldr = r.cout; }
+        if (only16(out, identity)) { d.out = out.d16; d.out_mode = 1; }
+        else { alloc32(out); d.out = out.data; d.out16 = out.d16; d.out_mode = 0; }
+        d.ldc = r.cout; d.N = N; d.H = Ho; d.W = Wo;
         add_conv(d, &out);
         add_stats(out);
       }
@@ -675,7 +697,7 @@ Plan* Unet::build_plan(int N) {
       const int T = x.H * x.W;
       add_coeff(x, nullptr, a.gn, -1);
       GnApplyDesc g;
-      if (x.d16 != nullptr) { g.x0 = x.d16; g.x0_half = true; } else g.x0 = x.data;
+      if (x.d16 != nullptr) { g.x0 = x.d16; g.x0_half = true; } else g.x0 = use32(x);
       g.C0 = a.C; g.N = N; g.H = x.H; g.W = x.W; g.mode = 0; g.silu = 0; g.out_act = s_a1;
       add_apply(g);
       {
@@ -696,7 +718,8 @@ Plan* Unet::build_plan(int N) {
         ConvDesc d;
         d.act0 = s_a2; d.C0 = a.C; d.taps0 = 1;
         d.weight = W8(a.proj.w_off); d.cout_pad = a.proj.cout_pad; d.cout = a.C; d.bias = Wf(a.proj.b_off);
-        d.residual = x.data; d.ldr = a.C;
+        d.residual = use32(x); d.ldr = a.C;
+        alloc32(out);
         d.out = out.data; d.out16 = out.d16; d.ldc = a.C; d.out_mode = 0; d.N = N; d.H = x.H; d.W = x.W;
         add_conv(d, &out);
         add_stats(out);
@@ -728,7 +751,7 @@ Plan* Unet::build_plan(int N) {
     // ---- output head: GN + SiLU + conv3x3 -> eps (fp32 NCHW) ----
     add_coeff(cur, nullptr, out_gn_, -1);
     GnApplyDesc go;
-    if (cur.d16 != nullptr) { go.x0 = cur.d16; go.x0_half = true; } else go.x0 = cur.data;
+    if (cur.d16 != nullptr) { go.x0 = cur.d16; go.x0_half = true; } else go.x0 = use32(cur);
     go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.out_act = s_a1;
     add_apply(go);
     if (create) {
@@ -751,6 +774,8 @@ Plan* Unet::build_plan(int N) {
     return bump.off;
   };
 
+  layout(nullptr, false);
+  collect = false;
   const size_t total = layout(nullptr, false);
   IVID_CHECK_CUDA(cudaMalloc(&pl->ws, total + 4096));
   pl->ws_bytes = total;
