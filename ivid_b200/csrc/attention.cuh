@@ -136,8 +136,14 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
-      const float m_new = fmaxf(m_run, mx * kScaleLog2);
+      // lazy online softmax: the reference maximum of a row only moves when the new maximum exceeds it by more than
+      // 2^kLazy (probabilities stay <= 2^kLazy, far inside fp16 range, and O / l is independent of the reference), and
+      // the in-place rescale of O is skipped whenever no row of the warp moved.
+      constexpr float kLazy = 8.0f;
+      const float m_cand = fmaxf(m_run, mx * kScaleLog2);
+      const float m_new = (m_cand - m_run > kLazy) ? m_cand : m_run;      // m_run = -inf on the first block: always taken
       const float alpha = exp2f(m_run - m_new);
+      const bool rescale = __any_sync(0xffffffffu, alpha != 1.0f);
       // pass 2: probabilities -> fp16 -> TMEM (A operand of P V).  P columns [c/2, c/2+16) overwrite S columns that
       // have already been consumed by this thread (its own TMEM lane), never the half still to be read.
       float lsum = 0.f;
@@ -158,7 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
       l_run = l_run * alpha + lsum;
       m_run = m_new;
-      if (j > 0) {
+      if (j > 0 && rescale) {
         // correction: rescale the running output in place (PV_{j-1} must have landed)
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();

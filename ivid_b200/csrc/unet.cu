@@ -710,7 +710,8 @@ Plan* Unet::build_plan(int N) {
       if (create) {
         AttnLaunch* l = attn_launch_create(s_qkv, N, T, a.C, s_a2);
         pl->attns.push_back(l);
-        pl->ops.tag("attention", 4.0 * N * (a.C / 64) * static_cast<double>(T) * T * 64, static_cast<double>(N) * T * a.C * 8);
+        pl->ops.tag("attention", 4.0 * N * (a.C / 64) * static_cast<double>(T) * T * 64, static_cast<double>(N) * T * a.C * 8,
+                    "T=" + std::to_string(T) + " heads=" + std::to_string(a.C / 64));
         pl->ops.push_back([l](cudaStream_t s) { attn_launch_run(l, s); });
       }
       Act out = new_act(a.C, x.H, x.W);

@@ -9,7 +9,7 @@ echo "launch list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 2 -c 2 \
     -o gpurun_out/prof_${TAG}_conv -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}_conv.log 2>&1
 echo "conv capture exit $?"
-ncu --set full --clock-control none --import-source on -k regex:"gn_apply_kernel|attention_kernel" -s 10 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"gn_apply|attention_kernel|film_table" -s 10 -c 8 \
     -o gpurun_out/prof_${TAG}_misc -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}_misc.log 2>&1
 echo "misc capture exit $?"
 ls -la gpurun_out/*.ncu-rep
