@@ -160,6 +160,29 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant conv kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*_conv_summary.json")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for k in json.load(open(files[-1])):
+        try:
+            b = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = k[key].split()
+                b += float(v.replace(",", "")) * unit[u]
+            tot += b
+            n += 1
+        except (KeyError, ValueError):
+            continue
+    if n == 0:
+        return None, None
+    return tot / n, f"{os.path.relpath(files[-1], ROOT)}: mean of {n} captured conv_gemm launches (conv1 / conv2 of the first 128x128 ResBlock)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,8 +334,10 @@ def main():
     d = prof[dom]
     ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
     step_ms_prof = sum(v["ms"] for v in prof.values())
+    traffic, traffic_src = _ncu_traffic()
     roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + ", bf16/fp16 dense sustained",
+                "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_unit": "DRAM bytes/launch", "traffic_source": traffic_src,
+                "peak_source": peaks["src"] + ", bf16/fp16 dense sustained",
                 "launches_per_step": d["launches"], "kernel_share_of_step": d["ms"] / step_ms_prof,
                 "families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,

@@ -4,11 +4,15 @@
 //                      GroupNorm32 statistics (reference adm.py:36-41) are later formed per group from these, which
 //                      is what makes GroupNorm over a *virtual* channel concat (groups straddling the seam,
 //                      adm.py:563 + :158) free of any concat copy.
-//   gn_coeff_kernel  : per-(sample, channel) affine y = x*A + B that folds mean/rstd, gamma/beta and the FiLM
-//                      scale/shift  h = GN(h)*(1+scale)+shift  (adm.py:216-217).
-//   gn_apply_kernel  : y = [SiLU](x*A+B) written as fp16 NHWC (the conv A operand), optionally through the ResBlock's
-//                      nearest-2x upsample / 2x2 average pool (adm.py:203-208), optionally also emitting the raw input
-//                      as fp16 (operand of the 1x1 skip conv) and/or as resampled fp32 (identity skip of up/down blocks).
+//                      Only used below 32 pixels per sample: everywhere else the producing conv's epilogue accumulates
+//                      the statistics.
+//   gn_prologue      : (device function, per block) per-(sample, channel) affine y = x*A + B that folds mean/rstd,
+//                      gamma/beta and the FiLM scale/shift  h = GN(h)*(1+scale)+shift  (adm.py:216-217).
+//   gn_apply_h16_kernel: y = [SiLU](x*A+B), fp16 NHWC sources (hidden tensor, fp16 copies of block outputs, virtual
+//                      concat of two) -> fp16 NHWC conv operand; the bulk of the traffic.
+//   gn_apply_kernel  : generic variant: fp32 sources, the ResBlock's nearest-2x upsample / 2x2 average pool
+//                      (adm.py:203-208), optional raw fp16 copy (operand of the 1x1 skip conv) and / or resampled fp32
+//                      copy (identity skip of up/down blocks).
 //   pack_input_kernel: NCHW fp32 network input -> NHWC fp16 padded to 64 channels (adm.py:557, x.type(dtype)).
 #pragma once
 #include "common.cuh"
