@@ -234,6 +234,56 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
   const int Ho = p.mode == 1 ? p.H * 2 : (p.mode == 2 ? p.H / 2 : p.H);
   const int Wo = p.mode == 1 ? p.W * 2 : (p.mode == 2 ? p.W / 2 : p.W);
   const int pix0 = bx * p.pix_per_block;
+  if (p.mode == 1) {
+    // nearest-2x upsample, source-centric (pix_per_block counts SOURCE pixels): each source item is loaded and activated
+    // once and written to its 2x2 output pixels (fp16 operand + the resampled fp32 identity skip)
+    const int npix_s = min(p.pix_per_block, p.H * p.W - pix0);
+    const int items_s = npix_s * c8;
+    constexpr int U = 4;
+    auto emit = [&](int it, const float (&raw)[8]) {
+      const int cg = it % c8;
+      const int pix = pix0 + it / c8;
+      const int hs = pix / p.W, ws = pix - hs * p.W;
+      float act[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(raw[j], s_ab[j * c8 + cg], s_ab[C + j * c8 + cg]);
+        if (p.silu) y = silu_f(y);
+        act[j] = y;
+      }
+      uint4 pk;
+      pk.x = pack_h2(act[0], act[1]); pk.y = pack_h2(act[2], act[3]);
+      pk.z = pack_h2(act[4], act[5]); pk.w = pack_h2(act[6], act[7]);
+      const float4 r0 = make_float4(raw[0], raw[1], raw[2], raw[3]), r1 = make_float4(raw[4], raw[5], raw[6], raw[7]);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t o = ((static_cast<size_t>(n) * Ho + 2 * hs + dy) * Wo + 2 * ws + dx) * C + cg * 8;
+          *reinterpret_cast<uint4*>(p.out_act + o) = pk;
+          if (p.out_raw32 != nullptr) { stg_f4(p.out_raw32 + o, r0); stg_f4(p.out_raw32 + o + 4, r1); }
+        }
+    };
+    int it0 = threadIdx.x;
+    for (; it0 + (U - 1) * 256 < items_s; it0 += U * 256) {
+      float raw[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int it = it0 + u * 256;
+        const int pix = pix0 + it / c8;
+        load8(p, n, pix / p.W, pix % p.W, (it % c8) * 8, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) emit(it0 + u * 256, raw[u]);
+    }
+    for (int it = it0; it < items_s; it += 256) {
+      float raw[8];
+      const int pix = pix0 + it / c8;
+      load8(p, n, pix / p.W, pix % p.W, (it % c8) * 8, raw);
+      emit(it, raw);
+    }
+    return;
+  }
   const int npix = min(p.pix_per_block, Ho * Wo - pix0);
   const int items = npix * c8;
   int it0 = threadIdx.x;

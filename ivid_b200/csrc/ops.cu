@@ -269,11 +269,17 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     const int small = std::max(1, 1024 / (C / 8));      // at least ~4 work items per thread
     p.pix_per_block = std::max(1, std::min(Ho * Wo, mode == 0 ? small : (mode == 2 ? std::max(by_wave / 4, small) : std::max(by_wave, small))));
   }
+  // the upsampling path walks SOURCE pixels (each written to its 2x2 outputs)
+  int pix_space = Ho * Wo;
+  if (d.mode == 1) {
+    pix_space = d.H * d.W;
+    p.pix_per_block = std::max(1, (p.pix_per_block + 3) / 4);
+  }
   {
     static const bool fwd = getenv("IVID_GN_FWD") != nullptr;
     p.reverse = fwd ? 0 : 1;
   }
-  dim3 grid((Ho * Wo + p.pix_per_block - 1) / p.pix_per_block, d.N);
+  dim3 grid((pix_space + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;
   if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
     if (256 % (C / 8) == 0) gn_apply_h16_kernel<true><<<grid, 256, smem, s>>>(p);
