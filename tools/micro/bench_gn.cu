@@ -66,6 +66,18 @@ __global__ void k_copy(const uint4* __restrict__ x, uint4* __restrict__ y, size_
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) y[i] = __ldg(x + i);
 }
 
+__global__ void k_fill(uint4* __restrict__ y, size_t n) {
+  const uint4 v = make_uint4(1, 2, 3, 4);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) y[i] = v;
+}
+__global__ void k_read(const uint4* __restrict__ x, uint4* __restrict__ y, size_t n) {
+  uint4 a = make_uint4(0, 0, 0, 0);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(x + i); a.x ^= v.x; a.y ^= v.y; a.z ^= v.z; a.w ^= v.w;
+  }
+  if (a.x == 0x12345678u) y[0] = a;
+}
+
 template <typename F>
 static float time_it(F f, int reps = 20) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -96,6 +108,12 @@ int main(int argc, char** argv) {
   {
     const float ms = time_it([&] { k_copy<<<sms * 8, 256>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), el / 8); });
     printf("%-34s : %.4f ms  %.0f GB/s\n", "plain copy (16B/thread grid-stride)", ms, gb / ms * 1e3);
+    const float msf = time_it([&] { k_fill<<<sms * 8, 256>>>(reinterpret_cast<uint4*>(y), el / 8); });
+    printf("%-34s : %.4f ms  %.0f GB/s\n", "pure write (16B/thread)", msf, el * 2.0 / 1e9 / msf * 1e3);
+    const float msm = time_it([&] { cudaMemsetAsync(y, 0, el * 2); });
+    printf("%-34s : %.4f ms  %.0f GB/s\n", "cudaMemset", msm, el * 2.0 / 1e9 / msm * 1e3);
+    const float msr = time_it([&] { k_read<<<sms * 8, 256>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), el / 8); });
+    printf("%-34s : %.4f ms  %.0f GB/s\n", "pure read (16B/thread)", msr, el * 2.0 / 1e9 / msr * 1e3);
     const float ms2 = time_it([&] { cudaMemcpyAsync(y, x, el * 2, cudaMemcpyDeviceToDevice); });
     printf("%-34s : %.4f ms  %.0f GB/s\n", "cudaMemcpy D2D", ms2, gb / ms2 * 1e3);
   }
