@@ -49,7 +49,7 @@ class Tables:
 
 def _ex(arr: np.ndarray, t: torch.Tensor, ndim: int) -> torch.Tensor:
     # samplers/utils.py:20-23: float64 table -> index -> float32 -> broadcast
-    r = torch.from_numpy(arr)[t].float()
+    r = torch.from_numpy(arr).to(t.device)[t].float()      # (the reference copies the table to t's device on every call)
     return r.view(-1, *([1] * (ndim - 1)))
 
 
