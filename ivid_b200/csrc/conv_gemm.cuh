@@ -27,6 +27,10 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tiles_n;
   int n_blocks;                // Cout_pad / BN
   int num_tiles;               // tiles_w*tiles_h*tiles_n*n_blocks
+  // Work list of a CTA (pair): items [0, full_items) are full BN-wide tiles; items [full_items, num_items) are the remaining
+  // tiles cut into two BN/2-wide halves each, so that the last, partially filled round of a small layer costs half a tile
+  // (wave quantisation on the 16x16 / 32x32 levels).  No split: full_items = num_items = num_tiles / kCtas.
+  int full_items, num_items;
   int seg_chunks[3];           // channels/64 of each K segment (0 = segment unused)
   int seg_taps[3];             // 9 (3x3) or 1 (1x1)
   int Cout;                    // valid output channels
@@ -49,6 +53,7 @@ struct ConvGemmParams {
 struct ConvMaps {
   CUtensorMap a[3];            // activation segments (fp16 NHWC)
   CUtensorMap b;               // packed weights
+  CUtensorMap bh;              // packed weights, half-width box (split tail items)
   CUtensorMap out, res;        // epilogue: output tile store, residual tile load
   CUtensorMap out16;           // optional fp16 copy of an fp32 output ([32 px][64 ch] boxes)
 };
@@ -122,7 +127,20 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   // work items of this CTA: tiles (kCtas == 1) or tile PAIRS of its cluster (kCtas == 2; CTA `rank` owns m-tile 2*pair+rank)
   const int w_first = (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int w_stride = (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int w_limit = p.num_tiles / kCtas;
+  const int w_limit = p.num_items;
+  // work item -> (pixel-tile index of the CTA (pair), first output column, width)
+  auto decode = [&](int w, int& mtp, int& colbase, int& ncols) {
+    int f = w, half = 0;
+    ncols = BN;
+    if (w >= p.full_items) {
+      const int hidx = w - p.full_items;
+      f = p.full_items + (hidx >> 1);
+      half = hidx & 1;
+      ncols = BN / 2;
+    }
+    mtp = f / p.n_blocks;
+    colbase = (f - mtp * p.n_blocks) * BN + half * (BN / 2);
+  };
 
   const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1] + p.seg_chunks[2] * p.seg_taps[2];
   const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -134,13 +152,17 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     // 2-CTA: every load of either CTA signals the LEADER's full barrier (its MMA thread consumes both halves)
     const uint32_t full0 = (kCtas == 2) ? mapa_cluster(smem_u32(&full_bar[0]), 0) : 0u;
     for (int w = w_first; w < w_limit; w += w_stride) {
-      const int nblk = w % p.n_blocks;
-      const int mt = (w / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
+      int mtp, colbase, ncols;
+      decode(w, mtp, colbase, ncols);
+      const int mt = mtp * kCtas + static_cast<int>(cta_rank);
       const int tn = mt / tiles_per_img;
       const int rem = mt - tn * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int tw = rem - th * p.tiles_w;
       const int n0 = tn * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
+      const bool full = ncols == BN;
+      const CUtensorMap* mapB = full ? &maps.b : &maps.bh;
+      const uint32_t b_bytes = full ? Cfg::B_BYTES : Cfg::B_BYTES / 2;
       int kcol = 0;
 #pragma unroll 1
       for (int seg = 0; seg < 3; ++seg) {
@@ -158,14 +180,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             if constexpr (kCtas == 2) {
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + b_bytes));
               const uint32_t bar = full0 + stage * 8;
               tma_load_4d_2sm(mapA, bar, sa, ch * 64, w0 + dx, h0 + dy, n0);
-              tma_load_2d_2sm(&maps.b, bar, sb, kcol, nblk * BN + static_cast<int>(cta_rank) * (BN / 2));
+              tma_load_2d_2sm(mapB, bar, sb, kcol, colbase + static_cast<int>(cta_rank) * (ncols / 2));
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + b_bytes);
               tma_load_4d(mapA, &full_bar[stage], sa, ch * 64, w0 + dx, h0 + dy, n0);
-              tma_load_2d(&maps.b, &full_bar[stage], sb, kcol, nblk * BN);
+              tma_load_2d(mapB, &full_bar[stage], sb, kcol, colbase);
             }
             kcol += 64;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -175,12 +197,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     }
   } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ===================================== MMA issuer (leader CTA only in 2-CTA mode) =====================================
-    constexpr uint32_t idesc = make_idesc_f16(128 * kCtas, BN, false, false, false);
+    constexpr uint32_t idesc_full = make_idesc_f16(128 * kCtas, BN, false, false, false);
+    constexpr uint32_t idesc_half = make_idesc_f16(128 * kCtas, BN >= 32 ? BN / 2 : BN, false, false, false);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = w_first; w < w_limit; w += w_stride) {
+      const uint32_t idesc = (w >= p.full_items) ? idesc_half : idesc_full;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -225,16 +249,25 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     const bool tma_res = p.epi_tma == 1 && p.residual != nullptr && !(p.debug & 2);
     uint32_t res_cnt = 0, res_issued = 0, out_cnt = 0;
     const uint32_t my_tiles = (w_first < w_limit) ? static_cast<uint32_t>((w_limit - w_first + w_stride - 1) / w_stride) : 0u;
-    const uint32_t total_seq = my_tiles * NCH;
+    // this CTA's items: first `my_full` full-width ones (NCH chunks each), then half-width ones (NCH / 2 chunks each)
+    const uint32_t my_full = (p.full_items > w_first) ? static_cast<uint32_t>((p.full_items - w_first + w_stride - 1) / w_stride) : 0u;
+    const uint32_t my_full_c = my_full < my_tiles ? my_full : my_tiles;
+    constexpr uint32_t NCHH = NCH >= 2 ? NCH / 2 : 1;
+    const uint32_t total_seq = my_full_c * NCH + (my_tiles - my_full_c) * NCHH;
     auto issue_res = [&](uint32_t seq) {      // lane 0: residual tile of chunk `seq` of this CTA's chunk stream
-      const int w2 = w_first + static_cast<int>(seq / NCH) * w_stride;
-      const int k2 = static_cast<int>(seq % NCH);
-      const int nblk2 = w2 % p.n_blocks, mt2 = (w2 / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
+      uint32_t item, k2u;
+      if (seq < my_full_c * NCH) { item = seq / NCH; k2u = seq % NCH; }
+      else { const uint32_t s2 = seq - my_full_c * NCH; item = my_full_c + s2 / NCHH; k2u = s2 % NCHH; }
+      const int w2 = w_first + static_cast<int>(item) * w_stride;
+      const int k2 = static_cast<int>(k2u);
+      int mtp2, colbase2, ncols2;
+      decode(w2, mtp2, colbase2, ncols2);
+      const int mt2 = mtp2 * kCtas + static_cast<int>(cta_rank);
       const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
       uint64_t* bar = &res_bar[seq & 1];
       mbar_arrive_expect_tx(bar, 4096);
-      tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, nblk2 * BN + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
+      tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
                   tn2 * p.TN + box_n0);
     };
     if constexpr (CH == 32) {
@@ -245,8 +278,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     }
     const uint32_t tmem_empty0 = (kCtas == 2) ? mapa_cluster(smem_u32(&tmem_empty[0]), 0) : 0u;
     for (int wi = w_first; wi < w_limit; wi += w_stride) {
-      const int nblk = wi % p.n_blocks;
-      const int mt = (wi / p.n_blocks) * kCtas + static_cast<int>(cta_rank);
+      int mtp, colbase, ncols;
+      decode(wi, mtp, colbase, ncols);
+      const int mt = mtp * kCtas + static_cast<int>(cta_rank);
       const int tn = mt / tiles_per_img;
       const int rem = mt - tn * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -263,11 +297,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
+        for (int c0 = 0; c0 < ncols; c0 += CH) {
           uint32_t r[CH];
           tmem_ld_32x32b_x16(taddr + c0, r);
           tc_wait_ld();
-          const int col0 = nblk * BN + c0;
+          const int col0 = colbase + c0;
           if (!valid || col0 >= p.Cout) continue;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
@@ -291,9 +325,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int k = 0; k < NCH; ++k) {
+        for (int k = 0; k < ncols / 32; ++k) {
           const int c0 = k * 32;
-          const int col0 = nblk * BN + c0;
+          const int col0 = colbase + c0;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           float4 b4[8];
@@ -367,8 +401,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         if (do_stats && p.TN == 1) {
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
           const int t = threadIdx.x - 128;
-          for (int c = t; c < BN; c += 128) {
-            const int col = nblk * BN + c;
+          for (int c = t; c < ncols; c += 128) {
+            const int col = colbase + c;
             if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
               float ssum = 0.f, qsum = 0.f;
 #pragma unroll
@@ -386,9 +420,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int k = 0; k < BN / 64; ++k) {
+        for (int k = 0; k < ncols / 64; ++k) {
           const int c0 = k * 64;
-          const int col0 = nblk * BN + c0;
+          const int col0 = colbase + c0;
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(taddr + c0, r0);
           tmem_ld_32x32b_x32(taddr + c0 + 32, r1);
@@ -440,8 +474,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         if (do_stats && p.TN == 1) {
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
           const int t = threadIdx.x - 128;
-          for (int c = t; c < BN; c += 128) {
-            const int col = nblk * BN + c;
+          for (int c = t; c < ncols; c += 128) {
+            const int col = colbase + c;
             if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
               float ssum = 0.f, qsum = 0.f;
 #pragma unroll
@@ -476,7 +510,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         const bool has_res = p.residual != nullptr && !(p.debug & 2);
         float4 res_nx[8], b4_nx;
         auto prefetch = [&](int c0n) {
-          const int colq_n = nblk * BN + c0n + cq * 4;
+          const int colq_n = colbase + c0n + cq * 4;
           const bool okc = colq_n < p.Cout;
           b4_nx = okc ? ldg_f4(p.bias + colq_n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -487,11 +521,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
+        for (int c0 = 0; c0 < ncols; c0 += CH) {
           uint32_t r[CH];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tc_wait_ld();
-          const int col0 = nblk * BN + c0;
+          const int col0 = colbase + c0;
           if (col0 >= p.Cout) continue;                   // padded output columns (warp-uniform)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -504,7 +538,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           const float4 b4 = b4_nx;
 #pragma unroll
           for (int i = 0; i < 8; ++i) res[i] = res_nx[i];
-          if (c0 + CH < BN) prefetch(c0 + CH);
+          if (c0 + CH < ncols) prefetch(c0 + CH);
           float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -557,8 +591,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           // combine the four epilogue warps (same sample when TN == 1), then one double atomic per (column, moment)
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
           const int t = threadIdx.x - 128;
-          for (int c = t; c < BN; c += 128) {
-            const int col = nblk * BN + c;
+          for (int c = t; c < ncols; c += 128) {
+            const int col = colbase + c;
             if (col < p.Cout && n_warp < p.N) {
               float ssum = 0.f, qsum = 0.f;
 #pragma unroll

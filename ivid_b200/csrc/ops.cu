@@ -112,6 +112,28 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   M.a[1] = d.C1 > 0 ? make_act_map(d.act1, d.N, d.H, d.W, d.C1, p.TW, p.TH, p.TN) : M.a[0];
   M.a[2] = d.C2 > 0 ? make_act_map(d.act2, d.N, d.H, d.W, d.C2, p.TW, p.TH, p.TN) : M.a[0];
   M.b = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / l->ctas);
+  M.bh = M.b;
+  // Work list: full tiles, and - when the last round of the persistent grid would be less than half full - its tiles as
+  // twice as many half-width items (see ConvGemmParams::full_items).  A half-width item costs ~0.6 of a full one.
+  {
+    const int T = p.num_tiles / l->ctas;
+    const int S = l->ctas == 2 ? sm_count() / 2 : sm_count();
+    p.full_items = T;
+    p.num_items = T;
+    static const bool split_ok = getenv("IVID_NO_TAILSPLIT") == nullptr;
+    if (split_ok && l->BN == 256 && T > S) {
+      const int F = (T / S) * S, R = T - F;
+      if (R > 0) {
+        const double old_cost = static_cast<double>((T + S - 1) / S);
+        const double new_cost = static_cast<double>(T / S) + 0.6 * static_cast<double>((2 * R + S - 1) / S);
+        if (new_cost < old_cost - 0.05) {
+          p.full_items = F;
+          p.num_items = F + 2 * R;
+          M.bh = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / 2 / l->ctas);
+        }
+      }
+    }
+  }
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
   M.out = M.a[0]; M.res = M.a[0]; M.out16 = M.a[0];
   p.out16 = 0;
@@ -145,7 +167,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   }
   // fused statistics are produced by the TMA epilogues only
   if (p.stats != nullptr && p.epi_tma == 0) throw Error(kErrInvalidArgument, "conv: fused statistics need a TMA epilogue (Cout % 64 == 0)");
-  l->grid = l->ctas == 2 ? 2 * std::min(p.num_tiles / 2, sm_count() / 2) : std::min(p.num_tiles, sm_count());
+  l->grid = l->ctas == 2 ? 2 * std::min(p.num_items, sm_count() / 2) : std::min(p.num_items, sm_count());
   return l;
 }
 void conv_launch_destroy(ConvLaunch* l) { delete l; }

@@ -32,6 +32,7 @@ CONV_CASES = [
     (1, 4, 4, 64, 64, 3),        # tiny spatial: TN=8 with N=1
     (2, 64, 64, 64, 16, 3),      # narrow Cout (BN=16 path, output head shape)
     (1, 128, 128, 256, 256, 3),  # the dominant shape of the large model
+    (2, 64, 64, 64, 768, 3),     # 96 tile pairs on 74 SM pairs: the last round runs as half-width items
 ]
 
 
@@ -69,6 +70,22 @@ def test_conv_skip_segment_residual_and_fp16_out():
     assert G.report("conv3x3 + identity residual", out2.permute(0, 3, 1, 2), ref2) < 2e-5
     out3 = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3, out_fp16=True)
     assert G.report("conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), F.conv2d(a.half().float(), w.half().float(), b, padding=1)) < 5e-4
+
+
+def test_conv_split_tail_residual_and_fp16_out():
+    """Layer whose persistent grid ends in a partial round (3 x 32 tile pairs on 74 SM pairs): half-width tail items
+    through the residual-prefetch epilogue and the fp16-output epilogue."""
+    rng = _rng(11)
+    N, H, W, Cin, C = 2, 64, 64, 64, 768
+    a = _t(rng, N, Cin, H, W)
+    w = _t(rng, C, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin)); b = _t(rng, C, scale=0.1)
+    res = _t(rng, N, C, H, W)
+    base = F.conv2d(a.half().float(), w.half().float(), b, padding=1)
+    an = a.half().permute(0, 2, 3, 1).contiguous().cuda()
+    out = G.conv2d(an, w, b, 3, residual=res.permute(0, 2, 3, 1).contiguous().cuda())
+    assert G.report("split tail: conv3x3 + residual", out.permute(0, 3, 1, 2), base + res) < 2e-5
+    out16 = G.conv2d(an, w, b, 3, out_fp16=True)
+    assert G.report("split tail: conv3x3 fp16 out", out16.float().permute(0, 3, 1, 2), base) < 5e-4
 
 
 GN_CASES = [
