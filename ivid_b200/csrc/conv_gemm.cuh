@@ -41,6 +41,7 @@ struct ConvGemmParams {
   const float* residual;       // fp32 NHWC or nullptr
   void* out;
   double* stats;               // optional [N][Cout][2] per-(sample, channel) sum / sum-of-squares of the output (GroupNorm)
+  int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
@@ -266,9 +267,16 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
       uint64_t* bar = &res_bar[seq & 1];
-      mbar_arrive_expect_tx(bar, 4096);
-      tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
-                  tn2 * p.TN + box_n0);
+      if (p.res_up) {
+        // the warp's 16 x 2 output pixels are the 2x2 replicas of 8 x 1 source pixels: a [32 ch][8][1][1] box (1 KB)
+        mbar_arrive_expect_tx(bar, 1024);
+        tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, (tw2 * p.TW) >> 1,
+                    (th2 * p.TH + box_h0) >> 1, tn2 * p.TN + box_n0);
+      } else {
+        mbar_arrive_expect_tx(bar, 4096);
+        tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
+                    tn2 * p.TN + box_n0);
+      }
     };
     if constexpr (CH == 32) {
       if (tma_res) {
@@ -350,7 +358,11 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             const int pos = lane * 8 + (j ^ (lane & 7));
             float4 v = make_float4(__uint_as_float(r[4 * j]) + b4[j].x, __uint_as_float(r[4 * j + 1]) + b4[j].y,
                                    __uint_as_float(r[4 * j + 2]) + b4[j].z, __uint_as_float(r[4 * j + 3]) + b4[j].w);
-            if (tma_res) { const float4 t = rb[pos]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+            if (tma_res) {
+              const int rrow = (lane & 15) >> 1;        // res_up: source pixel of this lane's output pixel
+              const float4 t = p.res_up ? rb[rrow * 8 + (j ^ rrow)] : rb[pos];
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
             if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the batch tail: clipped by TMA, zero for the statistics
             ob[pos] = v;
             if (want16) {

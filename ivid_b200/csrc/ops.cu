@@ -59,6 +59,12 @@ static void set_conv_attr() {
   });
 }
 
+bool conv_can_res_up(int W, int cout) {
+  static const int dbg = [] { const char* e = getenv("IVID_CONV_DEBUG"); return e ? atoi(e) : 0; }();
+  static const bool off = getenv("IVID_NO_RES_UP") != nullptr;
+  return W >= 16 && cout % 32 == 0 && !(dbg & 16) && !off;
+}
+
 bool conv_can_out16(int cout) {
   static const int dbg = [] { const char* e = getenv("IVID_CONV_DEBUG"); return e ? atoi(e) : 0; }();
   static const bool off = getenv("IVID_NO_OUT16") != nullptr;
@@ -147,7 +153,18 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
       return make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     };
     M.out = f32_map(d.out, d.ldc);
-    if (d.residual != nullptr) M.res = f32_map(d.residual, d.ldr);
+    p.res_up = 0;
+    if (d.residual != nullptr && d.residual_up) {
+      IVID_REQUIRE(p.TW == 16 && bh == 2 && d.H % 2 == 0, "conv: upsampled residual needs 16-pixel-wide tiles");
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.ldr), static_cast<uint64_t>(d.W / 2), static_cast<uint64_t>(d.H / 2), static_cast<uint64_t>(d.N)};
+      const uint64_t str[3] = {static_cast<uint64_t>(d.ldr) * 4, static_cast<uint64_t>(d.W / 2) * d.ldr * 4,
+                               static_cast<uint64_t>(d.H / 2) * (d.W / 2) * d.ldr * 4};
+      const uint32_t box[4] = {32, 8, 1, 1};
+      M.res = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.residual), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      p.res_up = 1;
+    } else if (d.residual != nullptr) {
+      M.res = f32_map(d.residual, d.ldr);
+    }
     p.epi_tma = 1;
     if (d.out16 != nullptr) {
       IVID_REQUIRE(d.cout % 64 == 0 && !(l->BN == 256 && l->ctas == 1), "conv: fp16 output copy needs Cout % 64 == 0");

@@ -23,6 +23,7 @@ struct ConvDesc {
   int cout = 0;                                            // valid output channels
   const float* bias = nullptr;                             // [cout_pad]
   const float* residual = nullptr; int ldr = 0;            // fp32 NHWC
+  bool residual_up = false;                                // residual is [N][H/2][W/2][ldr]: added through a nearest-2x upsample (conv_can_res_up)
   void* out = nullptr; int ldc = 0; int out_mode = 0;      // 0 fp32 NHWC, 1 fp16 NHWC, 2 fp32 NCHW
   double* stats = nullptr;                                 // optional fused GroupNorm statistics of the output [N][cout][2]
   int N = 0, H = 0, W = 0;
@@ -37,6 +38,8 @@ void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s);   // s
 int conv_pick_bn(int cout_pad, int m_tiles = 0);          // m_tiles > 0: wave-quantisation aware choice
 // whether a conv with this many (unpadded) output channels can also emit the fp16 copy of its fp32 NHWC output
 bool conv_can_out16(int cout);
+// whether the conv epilogue can add a half-resolution residual through a nearest-2x upsample (output width W, Cout)
+bool conv_can_res_up(int W, int cout);
 bool conv_can_fuse_stats(int H, int W);                    // epilogue statistics need >= 32 pixels of one sample per warp
 int conv_pad_cout(int cout);
 

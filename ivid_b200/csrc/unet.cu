@@ -638,7 +638,9 @@ Plan* Unet::build_plan(int N) {
       const int Ho = r.mode == 1 ? H * 2 : (r.mode == 2 ? H / 2 : H);
       const int Wo = r.mode == 1 ? Wd * 2 : (r.mode == 2 ? Wd / 2 : Wd);
       const bool identity = !r.skip_conv;
-      const bool need_xr = identity && (r.mode != 0 || x1 != nullptr);   // resampled / concatenated identity skip
+      // nearest-2x upsample of the identity skip is applied by the conv epilogue itself when the tile geometry allows it
+      const bool res_up = identity && r.mode == 1 && x1 == nullptr && conv_can_res_up(Wo, r.cout);
+      const bool need_xr = identity && (r.mode != 0 || x1 != nullptr) && !res_up;   // resampled / concatenated identity skip
       // GN1 + SiLU (+ resample) -> a1 ; raw fp16 copy for the 1x1 skip conv ; raw fp32 for resampled identity skip
       add_coeff(x0, x1, r.gn1, -1);
       GnApplyDesc g1;
@@ -683,7 +685,7 @@ Plan* Unet::build_plan(int N) {
           if (x1 != nullptr) { d.act2 = x1->d16; d.C2 = x1->C; d.taps2 = 1; }
         } else if (r.skip_conv) { d.act1 = s_xh; d.C1 = r.cin; d.taps1 = 1; }
         d.weight = W8(r.conv2.w_off); d.cout_pad = r.conv2.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv2.b_off);
-        if (identity) { d.residual = need_xr ? s_xr : use32(x0); d.ldr = r.cout; }
+        if (identity) { d.residual = need_xr ? s_xr : use32(x0); d.ldr = r.cout; d.residual_up = res_up; }
         if (only16(out, identity)) { d.out = out.d16; d.out_mode = 1; }
         else { alloc32(out); d.out = out.data; d.out16 = out.d16; d.out_mode = 0; }
         d.ldc = r.cout; d.N = N; d.H = Ho; d.W = Wo;
