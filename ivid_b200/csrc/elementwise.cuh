@@ -100,7 +100,6 @@ struct GnApplyParams {
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
   int pix_per_block;
-  int reverse;                          // 1: blocks walk samples / pixel chunks from the end (see gn_block_pos)
   __half* out_act;                      // fp16 [N][Ho][Wo][C]
   __half* out_raw16;                    // optional fp16 raw copy (same-resolution only) [N][H][W][C]
   float* out_raw32;                     // optional fp32 raw (resampled) [N][Ho][Wo][C]
@@ -124,13 +123,10 @@ __device__ __forceinline__ void load8(const GnApplyParams& p, int n, int h, int 
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// Block -> (sample, pixel chunk).  Blocks are dispatched in increasing linear order; with reverse = 1 the first blocks take
-// the LAST samples / pixels.  The producing conv wrote its output in ascending order, so the tail of the tensor is what
-// is still in the 126 MB L2 when this kernel starts; and this kernel then finishes on the head of its output, which is
-// where the consuming conv (ascending) starts reading.
-__device__ __forceinline__ void gn_block_pos(const GnApplyParams& p, int& n, int& bx) {
-  n = p.reverse ? static_cast<int>(gridDim.y - 1 - blockIdx.y) : static_cast<int>(blockIdx.y);
-  bx = p.reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+// Block -> (sample, pixel chunk)
+__device__ __forceinline__ void gn_block_pos(const GnApplyParams&, int& n, int& bx) {
+  n = static_cast<int>(blockIdx.y);
+  bx = static_cast<int>(blockIdx.x);
 }
 
 // statistics -> per-channel affine (see above) for sample blockIdx.y, left in shared memory for the whole block

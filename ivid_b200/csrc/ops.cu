@@ -314,10 +314,6 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     pix_space = d.H * d.W;
     p.pix_per_block = std::max(1, (p.pix_per_block + 3) / 4);
   }
-  {
-    static const bool fwd = getenv("IVID_GN_FWD") != nullptr;
-    p.reverse = fwd ? 0 : 1;
-  }
   dim3 grid((pix_space + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;
   if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
