@@ -149,6 +149,8 @@ typedef struct {
   double atol;      /* sample.py:261 */
   double rtol;      /* sample.py:262 */
   int erode_rgb;    /* sample.py:263 */
+  double padding;   /* depth_to_mesh padding: 0 = 'frustum' (sample.py:131: ring pushed out one pixel and pulled to z = -0.1);
+                       > 0 = that many pixels, ring not pulled (inference/utils.py:107 load_scene uses 32 for free-view rendering) */
 } ivid_warp_params_t;
 
 /* [AggregationRenderer(render_size, image_size, near, far) for _ in range(batch)]  (sample.py:50) */

@@ -56,7 +56,7 @@ class StepArgsT(Structure):
 
 class WarpParamsT(Structure):
     _fields_ = [("fov_deg", c_double), ("near", c_double), ("far", c_double), ("atol", c_double), ("rtol", c_double),
-                ("erode_rgb", c_int)]
+                ("erode_rgb", c_int), ("padding", c_double)]
 
 
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against the header

@@ -379,7 +379,8 @@ struct MeshParams {
   int B, n;                   // n = image size (128); grid is (n+2)^2
   float near_f, far_f;        // linearize_depth planes (float32 casts)
   float fn_f, nf_f;           // (far-near), near*far as float32
-  double focal, step;         // 0.5/tan(fov/2), plane/n
+  double focal, step;         // 0.5/tan(fov/2), plane/n (frustum) or (padding*plane)/n
+  int frustum;                // 1: padding='frustum' (ring pulled to z = -0.1); 0: numeric padding
   double lin0, lin_step;      // np.linspace(0.5/n, 1-0.5/n, n): start, step
   double lin_last;
   float atol_f, rtol_f;
@@ -450,10 +451,12 @@ __global__ void mesh_points_kernel(const MeshParams p) {
   if (R == m - 1) pt[1] -= p.step * dzd;
   if (C == 0) pt[0] -= p.step * dzd;
   if (C == m - 1) pt[0] += p.step * dzd;
-  if (R == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
-  if (R == m - 1) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
-  if (C == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
-  if (C == m - 1) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
+  if (p.frustum) {
+    if (R == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
+    if (R == m - 1) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
+    if (C == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
+    if (C == m - 1) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
+  }
   const size_t o = static_cast<size_t>(b) * m * m + idx;
   for (int j = 0; j < 3; ++j) { p.pts[o * 3 + j] = pt[j]; p.nrm[o * 3 + j] = nv[j]; }
   p.dep[o] = dz;
@@ -798,7 +801,8 @@ class Warp {
     p.nf_f = static_cast<float>(wp.near * wp.far);
     const double fov = wp.fov_deg * (M_PI / 180.0);      // np.deg2rad
     p.focal = 0.5 / std::tan(0.5 * fov);
-    p.step = (2 * std::tan(0.5 * fov)) / n_;
+    p.frustum = wp.padding > 0.0 ? 0 : 1;
+    p.step = p.frustum ? (2 * std::tan(0.5 * fov)) / n_ : (wp.padding * (2 * std::tan(0.5 * fov))) / n_;   // utils.py:190,201
     p.lin0 = 0.5 / n_; p.lin_last = 1 - 0.5 / n_;
     p.lin_step = (p.lin_last - p.lin0) / (n_ - 1);
     p.atol_f = static_cast<float>(wp.atol); p.rtol_f = static_cast<float>(wp.rtol);

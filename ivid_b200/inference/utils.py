@@ -63,8 +63,9 @@ def save_scene(path, meshes, colors):
     np.savez_compressed(path, data=np.array(data, dtype=object))
 
 
-def load_scene(path):
-    """-> list of edict(color [H,W,3] float in [0,1], depth [H,W,1] float32 linear, fov, modelview)."""
+def load_scene_views(path):
+    """Host-only decode of a scene file -> list of edict(color [H,W,3] float in [0,1], depth [H,W,1] float32 linear, fov,
+    modelview)."""
     data = np.load(path, allow_pickle=True)["data"]
     out = []
     for d in data:
@@ -73,3 +74,29 @@ def load_scene(path):
         depth = np.frombuffer(np.ascontiguousarray(_unpng(d["depth"])).tobytes(), dtype=np.float32).reshape(n, n, 1)
         out.append(edict(color=col, depth=depth, fov=d["fov"], modelview=d["modelview"]))
     return out
+
+
+def load_scene(path, atol=0.03, rtol=0.03, erode_rgb=3):
+    """(meshes, colors) as the reference's load_scene (inference/utils.py:104-113): every stored view is re-meshed with
+    depth_to_mesh(depth, 32, fov, modelview, atol, rtol, erode_rgb, cal_normal=True) — numeric padding, for free-view
+    rendering.  The meshing runs on the GPU (rgbd_3d.utils.depth_to_mesh)."""
+    from ..rgbd_3d import utils as r3d
+    views = load_scene_views(path)
+    meshes = [r3d.depth_to_mesh(v.depth, 32, v.fov, v.modelview, atol=atol, rtol=rtol, erode_rgb=erode_rgb, cal_normal=True) for v in views]
+    return meshes, [v.color for v in views]
+
+
+def colorize_depth(depth, min=-1, max=1):      # noqa: A002 - the reference's argument names (inference/utils.py:25)
+    """Inferno colour map of a depth image or batch (numpy HW / NHW or torch), near = bright; output in [min, max]."""
+    import cv2
+    is_tensor = isinstance(depth, torch.Tensor)
+    d = depth.detach().cpu().numpy() if is_tensor else np.asarray(depth)
+    d = d.squeeze()
+    if d.ndim == 2:
+        d = d[None]
+    d = np.clip(1 - (d - min) / (max - min), 0, 1)
+    maps = [cv2.cvtColor(cv2.applyColorMap((img * 255).astype(np.uint8), cv2.COLORMAP_INFERNO), cv2.COLOR_BGR2RGB) for img in d]
+    out = np.stack(maps, axis=0) / 255
+    if is_tensor:
+        out = torch.from_numpy(out).permute(0, 3, 1, 2).float()
+    return (out * (max - min) + min).squeeze()

@@ -16,8 +16,10 @@ from .glm_compat import as_matrix
 __all__ = ["AggregationRenderer", "DeviceWarp", "warp_params"]
 
 
-def warp_params(fov=45, near=0.5, far=100, atol=0.02, rtol=0.02, erode_rgb=2) -> _lib.WarpParamsT:
+def warp_params(fov=45, near=0.5, far=100, atol=0.02, rtol=0.02, erode_rgb=2, padding=0.0) -> _lib.WarpParamsT:
+    """padding: 0 = 'frustum' (sampling path), > 0 = numeric padding in pixels (free-view rendering, load_scene)."""
     p = _lib.WarpParamsT()
+    p.padding = float(padding)
     p.fov_deg, p.near, p.far = float(fov), float(near), float(far)
     p.atol = 0.0 if atol is None else float(atol)
     p.rtol = 0.0 if rtol is None else float(rtol)
@@ -64,6 +66,8 @@ class AggregationRenderer(_Native):
     def render(self, meshes, colors, modelview, fov=45.0, is_autoregressive=False, verbose=False, tqdm_args={}):
         """Render the aggregated view(s) (reference moderngl_renderer.py:260-340).  numpy HWC in / out."""
         L = _lib.lib()
+        if not is_autoregressive:
+            _lib.check(L.ivid_warp_reset(self._handle))      # a fresh set of source views (e.g. the next scene of render.py)
         for i, mesh in enumerate(meshes):
             if is_autoregressive and i != len(meshes) - 1:
                 continue      # earlier views were uploaded by earlier calls (moderngl_renderer.py:281-283)

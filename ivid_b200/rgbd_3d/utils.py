@@ -48,9 +48,11 @@ def _scratch_renderer(n, device=0):
 
 def depth_to_mesh(depth, padding=None, fov=45, modelview=None, atol=None, rtol=None, erode_rgb=None, cal_normal=False):
     """Convert a linearised depth image [H,W,1] to the padded, flagged triangle mesh of the reference (utils.py:144-260).
-    Only the configuration the sampling path uses is implemented: padding='frustum', cal_normal=True, a modelview."""
-    if padding != "frustum" or not cal_normal or modelview is None:
-        raise NotImplementedError("depth_to_mesh: only padding='frustum', cal_normal=True with a modelview is on the sampling path")
+    Implemented: padding='frustum' (inference/sample.py) or a positive number of pixels (inference/utils.py:load_scene),
+    cal_normal=True, with a modelview."""
+    numeric = isinstance(padding, (int, float)) and not isinstance(padding, bool) and padding > 0
+    if not (padding == "frustum" or numeric) or not cal_normal or modelview is None:
+        raise NotImplementedError("depth_to_mesh: padding must be 'frustum' or a positive number, with cal_normal=True and a modelview")
     d = np.ascontiguousarray(np.asarray(depth, dtype=np.float32).reshape(depth.shape[0], depth.shape[1]))
     n = d.shape[0]
     r = _scratch_renderer(n, torch.cuda.current_device())
@@ -58,7 +60,7 @@ def depth_to_mesh(depth, padding=None, fov=45, modelview=None, atol=None, rtol=N
     vb = np.empty((V, 9), np.float32)
     faces = np.empty((F, 3), np.uint32)
     mv = np.ascontiguousarray(as_matrix(modelview), dtype=np.float32)
-    p = warp_params(fov, 1.0, 2.0, atol, rtol, erode_rgb)     # near/far unused: the depth is already linear
+    p = warp_params(fov, 1.0, 2.0, atol, rtol, erode_rgb, padding=float(padding) if numeric else 0.0)   # near/far unused: depth is linear
     _lib.check(_lib.lib().ivid_warp_mesh_from_depth(r._handle, d.ctypes.data, mv.ctypes.data, ctypes.byref(p), vb.ctypes.data,
                                                     faces.ctypes.data, r._stream()))
     return edict({

@@ -120,8 +120,10 @@ def cal_depth_normal(points):
     return n / np.linalg.norm(n, axis=-1, keepdims=True)
 
 
-def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb=None):
-    """depth_to_mesh(depth, padding='frustum', cal_normal=True, ...) — the only mode inference/sample.py uses (:129-138)."""
+def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb=None, padding="frustum"):
+    """depth_to_mesh(depth, padding, cal_normal=True, ...) (utils.py:144-260).  padding='frustum' is what
+    inference/sample.py uses (:129-138); a number (pixels the border ring is pushed out by, ring not pulled to the near
+    plane) is what inference/utils.py:load_scene uses for free-view rendering (padding=32)."""
     n = depth.shape[0]
     plane = 2 * np.tan(0.5 * np.deg2rad(fov))
     points, uv = unproject(depth, fov)
@@ -129,15 +131,19 @@ def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb
     ret = AttrDict(depth=depth, fov=fov, modelview=modelview)
     pad = ((1, 1), (1, 1), (0, 0))
     points, uv, depth, normal = (np.pad(a, pad, "edge") for a in (points, uv, depth, normal))
-    step = plane / n
+    frustum = isinstance(padding, str)
+    if frustum and padding != "frustum":
+        raise NotImplementedError(padding)
+    step = plane / n if frustum else padding * plane / n
     points[0, :, 1] += step * depth[0, :, 0]
     points[-1, :, 1] -= step * depth[-1, :, 0]
     points[:, 0, 0] -= step * depth[:, 0, 0]
     points[:, -1, 0] += step * depth[:, -1, 0]
-    points[0, :] *= -0.1 / points[0, :, 2:]
-    points[-1, :] *= -0.1 / points[-1, :, 2:]
-    points[:, 0] *= -0.1 / points[:, 0, 2:]
-    points[:, -1] *= -0.1 / points[:, -1, 2:]
+    if frustum:
+        points[0, :] *= -0.1 / points[0, :, 2:]
+        points[-1, :] *= -0.1 / points[-1, :, 2:]
+        points[:, 0] *= -0.1 / points[:, 0, 2:]
+        points[:, -1] *= -0.1 / points[:, -1, 2:]
     ring = np.zeros_like(depth, dtype=bool)
     ring[0, :] = ring[-1, :] = ring[:, 0] = ring[:, -1] = True
     n += 2

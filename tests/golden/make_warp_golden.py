@@ -111,6 +111,24 @@ def main():
     print(f"[prop] self-reprojection: max colour err {err:.2e}, max depth err {zerr:.2e}")
     assert err < 1e-6 and zerr < 2e-3
 
+    # --- numeric padding (inference/utils.py:load_scene -> depth_to_mesh(depth, 32, ...), free-view rendering) ---
+    meshes_pad = []
+    for rgbd, mv in zip(rgbds, views[:2]):
+        d_lin = warp_ref.linearize_depth(rgbd[:, :, 3:], near, far)
+        m_ref = ref.depth_to_mesh(d_lin, 32, fov, mv, atol=atol, rtol=rtol, erode_rgb=erode_rgb, cal_normal=True)
+        m_or = warp_ref.depth_to_mesh(d_lin, fov=fov, modelview=mv, atol=atol, rtol=rtol, erode_rgb=erode_rgb, padding=32)
+        for k in ["position", "normal", "uv", "flag"]:
+            assert np.array_equal(m_ref.vertices[k], m_or.vertices[k]), k
+        assert np.array_equal(m_ref.faces, m_or.faces)
+        meshes_pad.append(m_or)
+    print("[pin] depth_to_mesh(padding=32): bit-identical to the reference")
+    for i, m in enumerate(meshes_pad):
+        vb = warp_ref.mesh_vertex_buffer(m)
+        out[f"meshpad{i}_colsum"] = vb.astype(np.float64).sum(0)
+        out[f"meshpad{i}_abssum"] = np.abs(vb.astype(np.float64)).sum(0)
+        out[f"meshpad{i}_flaghist"] = np.bincount(vb[:, 8].astype(np.int64), minlength=8)
+        out[f"meshpad{i}_faces_sum"] = np.array([m.faces.astype(np.int64).sum(), (m.faces.astype(np.int64) * np.arange(1, 4)).sum()])
+
     for i, r in enumerate(rgbds):
         out[f"rgbd{i}"] = r
     out["views"] = np.stack(views)

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ivid_b200.inference import build_modelviews, load_scene, parse_int_list, reorder, save_scene, shard
+from ivid_b200.inference import (build_modelviews, colorize_depth, load_scene_views, parse_int_list, random_views, reorder,
+                                 save_scene, shard, swing_trajectory)
 from ivid_b200.utils import edict
 
 
@@ -49,11 +50,47 @@ def test_scene_roundtrip(tmp_path):
     colors = [rng.uniform(0, 1, (16, 16, 3)).astype(np.float32) for _ in range(2)]
     p = os.path.join(tmp_path, "scene.npz")
     save_scene(p, meshes, colors)
-    back = load_scene(p)
+    back = load_scene_views(p)
     for m, c, b in zip(meshes, colors, back):
         assert np.array_equal(b.depth, m.depth)                                          # float32 bits survive the RGBA8 PNG
         assert np.array_equal((np.clip(c * 255, 0, 255)).astype(np.uint8), np.round(b.color * 255).astype(np.uint8))
         assert b.fov == 45
+
+
+def test_free_view_trajectories():
+    """inference/render.py:43-61: cameras on the unit sphere looking at the origin."""
+    tr = swing_trajectory(9)
+    assert len(tr) == 9
+    for mv in tr:
+        m = np.asarray(mv, dtype=np.float64)
+        R, t = m[:3, :3], m[:3, 3]
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-6) and abs(np.linalg.det(R) - 1) < 1e-6
+        eye = -R.T @ t
+        assert abs(np.linalg.norm(eye) - 1) < 1e-6                     # unit sphere
+        assert np.allclose(R @ (0 - eye), [0, 0, -1], atol=1e-6)        # looks at the origin down -z
+    assert np.allclose(tr[0], tr[-1], atol=1e-6)                        # t = 0 and t = 2 pi coincide
+    e0 = -np.asarray(tr[0])[:3, :3].T @ np.asarray(tr[0])[:3, 3]
+    assert np.allclose(e0, [np.sin(0.6), 0, np.cos(0.6)], atol=1e-6)    # yaw 0.6, pitch 0 at t = 0
+    a, b = random_views(4, seed=3), random_views(4, seed=3)
+    assert len(a) == 4 and all(len(v) == 1 for v in a)
+    assert all(np.array_equal(x[0], y[0]) for x, y in zip(a, b))
+    for v in a:
+        m = np.asarray(v[0], dtype=np.float64)
+        eye = -m[:3, :3].T @ m[:3, 3]
+        yaw, pitch = np.arctan2(eye[0], eye[2]), np.arcsin(eye[1])
+        assert abs(yaw) <= 0.6 + 1e-6 and abs(pitch) <= 0.15 + 1e-6
+
+
+def test_colorize_depth():
+    import cv2
+    d = np.linspace(0, 1, 32 * 32, dtype=np.float32).reshape(32, 32)
+    c = colorize_depth(d, min=0, max=1)
+    assert c.shape == (32, 32, 3) and c.min() >= 0 and c.max() <= 1
+    ref = cv2.cvtColor(cv2.applyColorMap((np.clip(1 - d, 0, 1) * 255).astype(np.uint8), cv2.COLORMAP_INFERNO), cv2.COLOR_BGR2RGB) / 255
+    assert np.array_equal(c, ref)
+    assert c[0, 0].sum() > c[-1, -1].sum()                 # near is bright
+    t = colorize_depth(torch.from_numpy(d)[None] * 2 - 1)   # torch in [-1,1] -> torch CHW in [-1,1]
+    assert tuple(t.shape) == (3, 32, 32) and float(t.min()) >= -1 and float(t.max()) <= 1
 
 
 def _free_port():

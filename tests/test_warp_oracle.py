@@ -34,6 +34,25 @@ def test_mesh_checksums(wg):
         assert m.faces.astype(np.int64).sum() == wg[f"mesh{i}_faces_sum"][0]
 
 
+def test_numeric_padding_mesh_checksums(wg):
+    """depth_to_mesh(depth, 32, ...) — the meshing of inference/utils.py:load_scene (free-view rendering): same grid, border
+    ring pushed out 32 pixels and NOT pulled to the near plane.  Pinned bit-identical to the reference by make_warp_golden."""
+    near, far, fov, atol, rtol, erode = (float(v) for v in wg["params"])
+    for i in range(2):
+        d = warp_ref.linearize_depth(wg[f"rgbd{i}"][:, :, 3:], near, far)
+        m = warp_ref.depth_to_mesh(d, fov=fov, modelview=wg["views"][i], atol=atol, rtol=rtol, erode_rgb=int(erode), padding=32)
+        vb = warp_ref.mesh_vertex_buffer(m)
+        assert np.allclose(vb.astype(np.float64).sum(0), wg[f"meshpad{i}_colsum"], rtol=1e-9, atol=1e-6)
+        assert np.allclose(np.abs(vb.astype(np.float64)).sum(0), wg[f"meshpad{i}_abssum"], rtol=1e-9, atol=1e-6)
+        assert np.array_equal(np.bincount(vb[:, 8].astype(np.int64), minlength=8), wg[f"meshpad{i}_flaghist"])
+        assert m.faces.astype(np.int64).sum() == wg[f"meshpad{i}_faces_sum"][0]
+        # differs from the frustum mesh only on the border ring
+        f = warp_ref.depth_to_mesh(d, fov=fov, modelview=wg["views"][i], atol=atol, rtol=rtol, erode_rgb=int(erode))
+        inner = np.ones((130, 130), bool); inner[0, :] = inner[-1, :] = inner[:, 0] = inner[:, -1] = False
+        assert np.array_equal(m.vertices.position.reshape(130, 130, 3)[inner], f.vertices.position.reshape(130, 130, 3)[inner])
+        assert not np.array_equal(m.vertices.position, f.vertices.position)
+
+
 def test_aggregate_conditions_matches_golden(wg):
     near, far, fov, atol, rtol, erode = (float(v) for v in wg["params"])
     ms, cs = _meshes(wg, 2)
