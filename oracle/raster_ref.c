@@ -9,6 +9,8 @@
  *              rgbd_3d/shaders/aggregation.fsh:19-52  fragment stage (view-angle weight, flags, back faces)
  *              rgbd_3d/shaders/aggregation.csh:12-44  cross-view accumulation, "farther wins" for low-confidence pixels
  *              rgbd_3d/shaders/clear.csh
+ *              rgbd_3d/moderngl_renderer.py:11-148 + shaders/simple.{vsh,fsh}  SimpleRenderer (training-pair warp):
+ *                 same GL state, no back-face discard, alpha = (edge flag varying > 0.999 ? 0 : 1)
  * Rasterisation rules that GL leaves to the implementation are fixed here (and mirrored by the CUDA kernels):
  *   - vertex stage in fp32, clip = (P*MV) * v with P*MV formed on the host in double and rounded to fp32
  *   - near-plane clipping in clip space (z + w >= 0), polygons split as a fan
@@ -74,7 +76,7 @@ static float shade_weight(const float* pos, const float* nrm, const float* cam, 
   return fmaxf(w, 1e-16f);
 }
 
-static void raster_tri(const Vtx* v, int S, const float* tex, int T, const float* cam, float* color_fb, float* depth_fb) {
+static void raster_tri(const Vtx* v, int S, const float* tex, int T, const float* cam, float* color_fb, float* depth_fb, int simple) {
   int64_t X[3], Y[3];
   float zw[3], iw[3];
   for (int i = 0; i < 3; ++i) {
@@ -127,7 +129,7 @@ static void raster_tri(const Vtx* v, int S, const float* tex, int T, const float
       const float c0 = b0 / bs, c1 = b1 / bs, c2 = b2 / bs;
       const size_t idx = (size_t)py * S + (size_t)px;
       const float pad = (c0 * v[0].pad + c1 * v[1].pad) + c2 * v[2].pad;
-      if (!front && pad > 0.001f) continue;                 /* discard: no depth write (aggregation.fsh:23) */
+      if (!simple && !front && pad > 0.001f) continue;      /* discard: no depth write (aggregation.fsh:23) */
       if (!(z < depth_fb[idx])) continue;                   /* depth func '<' */
       depth_fb[idx] = z;
       float* o = color_fb + idx * 4;
@@ -146,7 +148,8 @@ static void raster_tri(const Vtx* v, int S, const float* tex, int T, const float
       ty = ty < 0 ? 0 : (ty > T - 1 ? T - 1 : ty);
       const float* tc = tex + ((size_t)ty * T + tx) * 3;
       o[0] = tc[0]; o[1] = tc[1]; o[2] = tc[2];
-      o[3] = shade_weight(pos, nrm, cam, edge, pad, ero);
+      o[3] = simple ? (edge > 0.999f ? 0.f : 1.f)          /* simple.fsh:19 */
+                    : shade_weight(pos, nrm, cam, edge, pad, ero);
     }
   }
 }
@@ -176,11 +179,42 @@ void raster_draw_mesh(const float* verts, int V, const uint32_t* faces, int F, c
     const int n = clip_near(in, poly);
     if (n >= 3) {
       Vtx t0[3] = {poly[0], poly[1], poly[2]};
-      raster_tri(t0, S, tex, T, cam, color_fb, depth_fb);
+      raster_tri(t0, S, tex, T, cam, color_fb, depth_fb, 0);
     }
     if (n == 4) {
       Vtx t1[3] = {poly[0], poly[2], poly[3]};
-      raster_tri(t1, S, tex, T, cam, color_fb, depth_fb);
+      raster_tri(t1, S, tex, T, cam, color_fb, depth_fb, 0);
+    }
+  }
+}
+
+/* SimpleRenderer.render for one modelview (moderngl_renderer.py:94-146): clear, draw TRIANGLES with simple.vsh / simple.fsh.
+ *   verts [V][6] float32: position(3) uv(2) flag(1)  (moderngl_renderer.py:113-117); v_is_edge = mod(flag, 2) */
+void raster_draw_simple(const float* verts, int V, const uint32_t* faces, int F, const float* tex, int T, const float* mvp,
+                        int S, float* color_fb, float* depth_fb) {
+  (void)V;
+  const float cam[3] = {0.f, 0.f, 0.f};
+  for (size_t i = 0; i < (size_t)S * S; ++i) { depth_fb[i] = 1.0f; }
+  memset(color_fb, 0, sizeof(float) * 4 * (size_t)S * S);
+  for (int f = 0; f < F; ++f) {
+    Vtx in[3], poly[4];
+    for (int k = 0; k < 3; ++k) {
+      const float* a = verts + (size_t)faces[f * 3 + k] * 6;
+      memset(&in[k], 0, sizeof(Vtx));
+      for (int r = 0; r < 4; ++r)
+        in[k].clip[r] = ((mvp[r * 4 + 0] * a[0] + mvp[r * 4 + 1] * a[1]) + mvp[r * 4 + 2] * a[2]) + mvp[r * 4 + 3];
+      in[k].pos[0] = a[0]; in[k].pos[1] = a[1]; in[k].pos[2] = a[2];
+      in[k].uv[0] = a[3]; in[k].uv[1] = a[4];
+      in[k].edge = fmodf(a[5], 2.0f);
+    }
+    const int n = clip_near(in, poly);
+    if (n >= 3) {
+      Vtx t0[3] = {poly[0], poly[1], poly[2]};
+      raster_tri(t0, S, tex, T, cam, color_fb, depth_fb, 1);
+    }
+    if (n == 4) {
+      Vtx t1[3] = {poly[0], poly[2], poly[3]};
+      raster_tri(t1, S, tex, T, cam, color_fb, depth_fb, 1);
     }
   }
 }

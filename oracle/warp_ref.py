@@ -120,35 +120,43 @@ def cal_depth_normal(points):
     return n / np.linalg.norm(n, axis=-1, keepdims=True)
 
 
-def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb=None, padding="frustum"):
-    """depth_to_mesh(depth, padding, cal_normal=True, ...) (utils.py:144-260).  padding='frustum' is what
-    inference/sample.py uses (:129-138); a number (pixels the border ring is pushed out by, ring not pulled to the near
-    plane) is what inference/utils.py:load_scene uses for free-view rendering (padding=32)."""
+def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb=None, padding="frustum", cal_normal=True):
+    """depth_to_mesh (utils.py:144-260).  padding='frustum' + normals is what inference/sample.py uses (:129-138); a number
+    (pixels the border ring is pushed out by, ring not pulled to the near plane) is what inference/utils.py:load_scene uses
+    for free-view rendering (padding=32); padding=None with cal_normal=False (plain n x n grid, no normals) is what
+    forward_backward_warp uses for its second mesh (utils.py:391-398)."""
     n = depth.shape[0]
     plane = 2 * np.tan(0.5 * np.deg2rad(fov))
     points, uv = unproject(depth, fov)
-    normal = cal_depth_normal(points)
+    normal = cal_depth_normal(points) if cal_normal else None
     ret = AttrDict(depth=depth, fov=fov, modelview=modelview)
-    pad = ((1, 1), (1, 1), (0, 0))
-    points, uv, depth, normal = (np.pad(a, pad, "edge") for a in (points, uv, depth, normal))
-    frustum = isinstance(padding, str)
-    if frustum and padding != "frustum":
-        raise NotImplementedError(padding)
-    step = plane / n if frustum else padding * plane / n
-    points[0, :, 1] += step * depth[0, :, 0]
-    points[-1, :, 1] -= step * depth[-1, :, 0]
-    points[:, 0, 0] -= step * depth[:, 0, 0]
-    points[:, -1, 0] += step * depth[:, -1, 0]
-    if frustum:
-        points[0, :] *= -0.1 / points[0, :, 2:]
-        points[-1, :] *= -0.1 / points[-1, :, 2:]
-        points[:, 0] *= -0.1 / points[:, 0, 2:]
-        points[:, -1] *= -0.1 / points[:, -1, 2:]
-    ring = np.zeros_like(depth, dtype=bool)
-    ring[0, :] = ring[-1, :] = ring[:, 0] = ring[:, -1] = True
-    n += 2
+    if padding is not None:
+        pad = ((1, 1), (1, 1), (0, 0))
+        points, uv, depth = (np.pad(a, pad, "edge") for a in (points, uv, depth))
+        if cal_normal:
+            normal = np.pad(normal, pad, "edge")
+        frustum = isinstance(padding, str)
+        if frustum and padding != "frustum":
+            raise NotImplementedError(padding)
+        step = plane / n if frustum else padding * plane / n
+        points[0, :, 1] += step * depth[0, :, 0]
+        points[-1, :, 1] -= step * depth[-1, :, 0]
+        points[:, 0, 0] -= step * depth[:, 0, 0]
+        points[:, -1, 0] += step * depth[:, -1, 0]
+        if frustum:
+            points[0, :] *= -0.1 / points[0, :, 2:]
+            points[-1, :] *= -0.1 / points[-1, :, 2:]
+            points[:, 0] *= -0.1 / points[:, 0, 2:]
+            points[:, -1] *= -0.1 / points[:, -1, 2:]
+        ring = np.zeros_like(depth, dtype=bool)
+        ring[0, :] = ring[-1, :] = ring[:, 0] = ring[:, -1] = True
+        n += 2
+    else:
+        ring = np.zeros_like(depth, dtype=bool)
     faces = triangulate(points)
-    points = points.reshape(-1, 3); normal = normal.reshape(-1, 3); uv = uv.reshape(-1, 2)
+    points = points.reshape(-1, 3); uv = uv.reshape(-1, 2)
+    if cal_normal:
+        normal = normal.reshape(-1, 3)
     depth = depth.reshape(-1, 1); ring = ring.reshape(-1, 1)
     disc = np.zeros_like(depth, dtype=bool)
     if atol is not None or rtol is not None:
@@ -157,7 +165,8 @@ def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb
     if modelview is not None:
         inv = inverse(modelview)
         points = (inv @ np.concatenate([points, np.ones((points.shape[0], 1))], axis=-1).T).T[:, :3]
-        normal = (inv[:3, :3] @ normal.T).T
+        if cal_normal:
+            normal = (inv[:3, :3] @ normal.T).T
     ero = np.zeros_like(depth, dtype=bool)
     if erode_rgb is not None and erode_rgb > 0:
         keep = np.ones_like(disc, dtype=np.float32)
@@ -166,7 +175,9 @@ def depth_to_mesh(depth, fov=45, modelview=None, atol=None, rtol=None, erode_rgb
         keep = cv2.erode(keep.reshape(n, n), np.ones((k, k))).reshape(-1, 1)
         ero[keep == 0] = True
     ret["faces"] = faces
-    ret["vertices"] = AttrDict(position=points, uv=uv, flag=1 * disc + 2 * ring + 4 * ero, normal=normal)
+    ret["vertices"] = AttrDict(position=points, uv=uv, flag=1 * disc + 2 * ring + 4 * ero)
+    if cal_normal:
+        ret["vertices"]["normal"] = normal
     return ret
 
 
@@ -243,6 +254,54 @@ class SoftwareAggregationRenderer:
         depth = (self.near * self.far / (self.far - depth * (self.far - self.near))).astype(np.float32)
         m = np.flip(agg_m.reshape(S, S, 2), axis=0)
         return AttrDict(color=color, depth=depth, mask_color=m[:, :, 1:] > 0.5, mask_depth=m[:, :, :1] > 0.5)
+
+
+class SoftwareSimpleRenderer:
+    """SimpleRenderer (moderngl_renderer.py:11-148, shaders/simple.{vsh,fsh}) on the CPU: one mesh, raw texture colours,
+    alpha = 0 on discontinuity edges and back faces; single modelview per call."""
+
+    def __init__(self, render_size=128, image_size=128, near=0.01, far=200.0, device=0):
+        self.render_size, self.image_size, self.near, self.far = render_size, image_size, near, far
+
+    def render(self, mesh, color, modelview, fov=45.0):
+        S, T = self.render_size, self.image_size
+        proj = perspective(np.deg2rad(fov), 1, self.near, self.far)
+        mvp = np.ascontiguousarray((proj.astype(np.float64) @ np.asarray(modelview, dtype=np.float64)).astype(np.float32))
+        v = mesh["vertices"]
+        vb = np.ascontiguousarray(np.concatenate([v["position"], v["uv"], v["flag"]], axis=-1).astype(np.float32))
+        faces = np.ascontiguousarray(mesh["faces"].astype(np.uint32))
+        tex = np.ascontiguousarray(np.asarray(color).astype(np.float32))
+        cfb = np.zeros((S * S, 4), np.float32); dfb = np.zeros((S * S,), np.float32)
+        _lib().raster_draw_simple(_fp(vb), vb.shape[0], _fp(faces), faces.shape[0], _fp(tex), T, _fp(mvp), S, _fp(cfb), _fp(dfb))
+        pix = np.flip(cfb.reshape(S, S, 4), axis=0)
+        depth = dfb.reshape(S, S, 1)
+        depth = self.near * self.far / (self.far - depth * (self.far - self.near))
+        depth = np.flip(depth, axis=0).astype(np.float32)
+        return AttrDict(color=pix[:, :, :3], depth=depth, mask=pix[:, :, 3:] > 0.5)
+
+
+def forward_backward_warp(renderer, rgbd, modelview1, modelview0=None, padding=None, fov=45, near=0.5, far=100, atol=0.02, rtol=0.02):
+    """forward_backward_warp (utils.py:335-417): view0 RGBD -> mesh -> rendered at view1 -> re-meshed -> rendered back at
+    view0; what survives both trips (and is not a depth edge) is the partial condition of a training pair."""
+    n = rgbd.shape[0]
+    ssaa = renderer.render_size // n
+    off = (ssaa - 1) // 2
+    if modelview0 is None:
+        modelview0 = view_on_sphere(0.0, 0.0)
+    resolve = lambda c: np.array(Image.fromarray(to8b(c)).resize((n, n), Image.Resampling.LANCZOS)) / 255.0
+    mesh0 = depth_to_mesh(linearize_depth(rgbd[:, :, 3:], near, far), fov=fov, modelview=modelview0, padding=padding, cal_normal=False)
+    res = renderer.render(mesh0, rgbd[:, :, :3], modelview1, fov)
+    color1 = resolve(res.color)
+    depth1 = res.depth[off::ssaa, off::ssaa, :]
+    mesh1 = depth_to_mesh(depth1, fov=fov, modelview=modelview1, atol=atol, rtol=rtol, padding=None, cal_normal=False)
+    res = renderer.render(mesh1, color1, modelview0, fov)
+    color = resolve(res.color)
+    depth = project_depth(res.depth[off::ssaa, off::ssaa, :], near, far)
+    mask = res.mask.reshape(n, ssaa, n, ssaa, 1).sum(axis=(1, 3)) > 0.75 * ssaa ** 2
+    mask &= depth_edge(depth, atol=atol, rtol=rtol)
+    color *= mask
+    depth *= mask
+    return AttrDict(color=color, depth=depth, mask=mask.astype(np.float32))
 
 
 def to8b(x):

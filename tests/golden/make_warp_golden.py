@@ -129,6 +129,24 @@ def main():
         out[f"meshpad{i}_flaghist"] = np.bincount(vb[:, 8].astype(np.int64), minlength=8)
         out[f"meshpad{i}_faces_sum"] = np.array([m.faces.astype(np.int64).sum(), (m.faces.astype(np.int64) * np.arange(1, 4)).sum()])
 
+    # --- training-pair warp (datasets/base.py:219-238): SimpleRenderer(384, 128, near=0.1, far=200) + forward_backward_warp
+    #     with padding = image_size; the reference's numpy / PIL steps run unmodified around the software SimpleRenderer ---
+    simple = warp_ref.SoftwareSimpleRenderer(128 * 3, 128, near=0.1, far=200)
+    d_lin = warp_ref.linearize_depth(rgbds[0][:, :, 3:], 0.5, 100)
+    for pad_arg, cal in [(None, False), (128, False)]:
+        m_ref = ref.depth_to_mesh(d_lin, padding=pad_arg, fov=fov, modelview=views[1], atol=0.02, rtol=0.02)
+        m_or = warp_ref.depth_to_mesh(d_lin, fov=fov, modelview=views[1], atol=0.02, rtol=0.02, padding=pad_arg, cal_normal=cal)
+        for k in ["position", "uv", "flag"]:
+            assert np.array_equal(m_ref.vertices[k], m_or.vertices[k]), (pad_arg, k)
+        assert np.array_equal(m_ref.faces, m_or.faces) and "normal" not in m_or.vertices
+    fb_ref = ref.forward_backward_warp(simple, rgbds[0], views[2], modelview0=views[0], padding=128, fov=fov, near=0.5, far=100)
+    fb_or = warp_ref.forward_backward_warp(simple, rgbds[0], views[2], modelview0=views[0], padding=128, fov=fov, near=0.5, far=100)
+    for k in ["color", "depth", "mask"]:
+        assert np.array_equal(fb_ref[k], fb_or[k]), k
+        out[f"fbw_{k}"] = np.asarray(fb_ref[k], dtype=np.float32)
+    print(f"[pin] depth_to_mesh(padding=None / 128, no normals) and forward_backward_warp: identical to the reference around the "
+          f"software SimpleRenderer; surviving mask {float(fb_ref['mask'].mean()):.3f}")
+
     for i, r in enumerate(rgbds):
         out[f"rgbd{i}"] = r
     out["views"] = np.stack(views)

@@ -87,3 +87,23 @@ def test_depth_roundtrip_and_glm(wg):
     assert np.allclose(warp_ref.inverse(mv)[:3, 3], [np.sin(0.3) * np.cos(-0.15), np.sin(-0.15), np.cos(0.3) * np.cos(-0.15)], atol=1e-6)
     P = warp_ref.perspective(np.deg2rad(45), 1, 0.01, 200)
     assert abs(P[0, 0] - 1 / np.tan(np.deg2rad(22.5))) < 1e-6 and P[3, 2] == -1
+
+
+def test_forward_backward_warp_matches_golden(wg):
+    """Training-pair warp (utils.py:335-417 around SimpleRenderer, datasets/base.py:219-238) — §8(f) row 3 oracle, pinned
+    against the reference's numpy / PIL steps by make_warp_golden.py."""
+    fov = float(wg["params"][2])
+    simple = warp_ref.SoftwareSimpleRenderer(384, 128, near=0.1, far=200)
+    r = warp_ref.forward_backward_warp(simple, wg["rgbd0"], wg["views"][2], modelview0=wg["views"][0], padding=128, fov=fov, near=0.5, far=100)
+    assert (np.asarray(r.mask, np.float32) != wg["fbw_mask"]).mean() < 1e-3
+    agree = (r.mask == wg["fbw_mask"])[..., 0]
+    assert np.abs(np.asarray(r.depth, np.float32) - wg["fbw_depth"])[agree].max() < 1e-5
+    assert np.abs(np.asarray(r.color, np.float32) - wg["fbw_color"])[agree].max() <= 1.0 / 255 + 1e-6
+    assert 0.5 < float(r.mask.mean()) < 0.95
+    # property: warping to the SAME camera and back keeps (almost) everything and reproduces the input
+    same = warp_ref.forward_backward_warp(simple, wg["rgbd0"], wg["views"][0], modelview0=wg["views"][0], padding=128, fov=fov, near=0.5, far=100)
+    keep = same.mask[..., 0] > 0
+    assert keep.mean() > 0.9
+    cerr = np.abs(same.color - wg["rgbd0"][:, :, :3])[keep]
+    assert np.quantile(cerr, 0.95) <= 2.0 / 255 + 1e-6 and cerr.max() < 0.1     # two 8-bit LANCZOS passes: ringing only at colour edges
+    assert np.abs(same.depth[..., 0] - wg["rgbd0"][:, :, 3])[keep].max() < 1e-5
