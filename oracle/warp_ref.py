@@ -6,6 +6,7 @@ CPU restatement of the reference's RGBD novel-view warp.
         linearize_depth :38-58     project_depth :61-67      image_uv :70-86       unproject :89-110
         triangulate :113-134       mask_discontinuity :137-141   depth_to_mesh :144-260
         cal_depth_normal :263-274  depth_edge :311-332       aggregate_conditions :420-477
+        forward_backward_warp :335-417 (training-pair warp; with SoftwareSimpleRenderer for moderngl_renderer.py:11-148)
   * the OpenGL rasteriser + GLSL shaders (moderngl_renderer.py:260-340, shaders/aggregation.*) cannot run here; they are
     restated in oracle/raster_ref.c — PARITY UNPINNED for that part (third-party GL driver arithmetic).
   * PyGLM is absent: lookAt / perspective / inverse are restated from the published GLM formulas (right-handed,
