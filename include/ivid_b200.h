@@ -164,7 +164,8 @@ int ivid_warp_num_views(const ivid_warp_t* w, int* n);
  * rgbd_dev: fp32 [batch,4,H,W] sampler output in [-1,1]; modelviews_host: [batch][16] (or one shared matrix). */
 int ivid_warp_add_view(ivid_warp_t* w, const float* rgbd_dev, const float* modelviews_host, int shared_modelview,
                        const ivid_warp_params_t* params, void* stream);
-/* rgbd_3d.utils.depth_to_mesh(depth, padding='frustum', cal_normal=True, ...) with numpy in/out (utils.py:144-260):
+/* rgbd_3d.utils.depth_to_mesh(depth, padding='frustum' | pixels (params->padding), cal_normal=True, ...) with numpy in/out
+ * (utils.py:144-260; the numeric padding is what inference/utils.py:107 load_scene uses for free-view rendering):
  * lin_depth_host [H][W] float32 linearised depth -> vertex buffer [(H+2)^2][9] and faces [2*(H+1)^2][3] on the host. */
 int ivid_warp_mesh_from_depth(ivid_warp_t* w, const float* lin_depth_host, const float* modelview_host,
                               const ivid_warp_params_t* params, float* verts_host, uint32_t* faces_host, void* stream);
