@@ -1,19 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the hot path (BASELINE.json configs[1]):
+"""bench.py — the hot path of BASELINE.json measured on its own configurations.
 
-    rgbd_imagenet_adm_128_large_cfg, unconditional view, DDPM 1000 steps + classifier-free guidance, batch 16 per GPU,
-    synthetic class labels + synthetic (seeded N(0,1/fan_in)) weights.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--batch B] [--full]
 
-One bench "step" = ONE denoising step of the whole batch: batch-2N UNet forward (both CFG halves) + fused eps mix +
-x_{t-1} update.  The 1000 steps of a sample are homogeneous (same kernels, same shapes; only the table row differs),
-so   samples/s = n_gpus * batch / (1000 * step_seconds)   — `denoise_steps_per_sample` is stated in `config`.
-`--full` times complete 1000-step samples instead (one bench step = one batch of finished samples).
+--config (default 2 = configs[1], the configuration the metric is quoted on):
+  2  rgbd_imagenet_adm_128_large_cfg, unconditional view, DDPM 1000 steps + classifier-free guidance 0.5, batch 16 / GPU
+  3  config 2 + a second view: viewset `random`, device warp, rgbd_imagenet_adm_128_large_cond (InpaintCFG) 50 guided DDIM steps
+  4  viewset `3x9`: 27 views / sample (26 conditional views, 351 source-view rasterisations), device warp
+  5  rgbd_imagenet_adm_256_128_small_sr (SuperResCFG), 256x256, 50 DDIM steps + guidance, batch 8 / GPU
+Synthetic class labels, synthetic seeded N(0, 1/fan_in) weights (the reference zero-initialises its last layers), synthetic
+smooth RGBD source views for the warp phase.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--full]
+One bench "step" = ONE denoising step of the whole batch of every network the configuration runs (batch-2N UNet forward
+with both guidance halves + fused eps mix + x_{t-1} update; configs 3/4: one step of the unconditional AND one of the
+conditional model).  The steps of a sample are homogeneous (same kernels, same shapes; only the table row differs), so
 
-N>1: launched by torchrun, one rank per GPU; samples shard by batch (no data-path collective), weights are packed on
-rank 0 and broadcast once with NCCL.  Timing: CUDA events on the launching stream, barrier + synchronize on both
-sides, max over ranks.
+    seconds / sample-batch = n_uncond_steps * t_uncond + n_cond_views * 50 * t_cond + t_warp        (stated in `config`)
+
+with t_warp the device time of the complete warp sequence of the view set (add_view + aggregate for every view), measured
+on its own with CUDA events.  `--full` runs the complete pipeline instead (one bench step = one finished sample batch).
+
+N>1: launched by torchrun, one rank per GPU; samples shard by batch (no data-path collective), weights are packed on rank 0
+and broadcast once with NCCL.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
+over ranks.  `--impl reference`: the reference's CPU path (oracle port; the Python reference cannot travel to the GPU
+box) on the host cores, same configuration, bounded sample.
 """
 from __future__ import annotations
 
@@ -32,12 +42,32 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-LARGE_CFG = dict(image_size=128, in_channels=4, out_channels=4, model_channels=256, num_res_blocks=2, num_classes=1000,
-                 has_null_class=True, channel_mult=[1, 1, 2, 3, 4], attention_resolutions=[32, 16, 8], num_groups=32,
-                 num_heads=None, num_head_channels=64, dropout=0.0, use_fp16=False)   # configs/rgbd_imagenet_adm_128_large_cfg.json
+_BASE = dict(out_channels=4, num_res_blocks=2, num_groups=32, num_heads=None, num_head_channels=64, dropout=0.0,
+             channel_mult=[1, 1, 2, 3, 4])
+MODELS = {   # backbone args of the reference's configs/*.json
+    "L": dict(_BASE, image_size=128, in_channels=4, model_channels=256, num_classes=1000, has_null_class=True,
+              attention_resolutions=[32, 16, 8], use_fp16=False),       # rgbd_imagenet_adm_128_large_cfg
+    "Lc": dict(_BASE, image_size=128, in_channels=10, model_channels=256, num_classes=1000, has_null_class=True,
+               attention_resolutions=[32, 16, 8], use_fp16=True),       # rgbd_imagenet_adm_128_large_cond
+    "SR": dict(_BASE, image_size=256, in_channels=8, model_channels=128, num_classes=1000, has_null_class=True,
+               attention_resolutions=[64, 32, 16], use_fp16=True),      # rgbd_imagenet_adm_256_128_small_sr
+}
+GFLOP_PER_FORWARD = {"L": 613.8, "Lc": 614.2, "SR": 697.8}        # per sample
 GUIDANCE = 0.5            # README.md:90 evaluation protocol
 DENOISE_STEPS = 1000
-GFLOP_PER_FORWARD = 613.8  # per sample
+COND_STEPS = 50
+WARP_KW = dict(fov=45, near=0.6, far=5, atol=0.03, rtol=0.03, erode_rgb=3)      # inference/sample.py:258-263
+
+WORKLOADS = {
+    2: dict(name="rgbd_imagenet_adm_128_large_cfg uncond, DDPM 1000 steps + classifier-free guidance 0.5 (BASELINE configs[1])",
+            batch=16, views=1, uncond="L", cond=None),
+    3: dict(name="imagenet128 uncond+cond iterative, viewset=random (2 views), 1000 DDPM + 50 DDIM steps, guidance 0.5 (BASELINE configs[2])",
+            batch=16, views=2, uncond="L", cond="Lc"),
+    4: dict(name="viewset=3x9 (27 views / sample, 26 conditional views x 50 DDIM steps), on-device RGBD warp, guidance 0.5 (BASELINE configs[3])",
+            batch=16, views=27, uncond="L", cond="Lc"),
+    5: dict(name="rgbd_imagenet_adm_256_128_small_sr super-resolution, 256x256, 50 DDIM steps + guidance 0.5 (BASELINE configs[4])",
+            batch=8, views=1, uncond=None, cond="SR"),
+}
 
 
 def _peaks():
@@ -49,15 +79,23 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def synth_rgbd(rng, n=128):
+    """Smooth synthetic RGBD view in [0,1] (z-buffer depth): a height field with one foreground blob."""
+    yy, xx = np.mgrid[0:n, 0:n] / n
+    z = 0.55 + 0.08 * np.sin(6.0 * xx + rng.uniform(0, 6)) * np.cos(5.0 * yy + rng.uniform(0, 6))
+    cx, cy, r = rng.uniform(0.35, 0.65), rng.uniform(0.35, 0.65), rng.uniform(0.15, 0.25)
+    z = np.where((xx - cx) ** 2 + (yy - cy) ** 2 < r ** 2, z - 0.18, z)
+    rgb = np.stack([0.5 + 0.5 * np.sin(9 * xx + i) * np.cos(7 * yy - i) for i in range(3)], axis=-1)
+    return np.concatenate([rgb, z[..., None]], axis=-1).astype(np.float32)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
-        self.index = index
+        self.rows, self.proc, self.index = [], None, index
 
     def start(self):
         try:
@@ -93,66 +131,136 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def seconds_per_batch(wl, t_u, t_c, t_warp):
+    """Composition rule of the module docstring (seconds per finished sample batch)."""
+    s = 0.0
+    if wl["uncond"]:
+        s += DENOISE_STEPS * t_u
+    if wl["cond"]:
+        s += max(wl["views"] - 1, 1 if wl["uncond"] is None else 0) * COND_STEPS * t_c
+    return s + t_warp
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle port of the reference path (the Python reference cannot travel)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_step_seconds(steps, warmup, budget_s=150.0):
-    from oracle import sampler_ref, unet_ref
+def pick_threads():
+    """Thread count that is actually fastest for a UNet-sized convolution on this host (oversubscribed SMT threads slow
+    oneDNN down).  Called before any timed CPU work, with warm-up."""
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # use the thread count that is actually fastest on this host (oversubscribed SMT threads slow oneDNN down)
     probe_x = torch.randn(1, 256, 128, 128)
     probe_w = torch.randn(256, 256, 3, 3)
     best, cores = None, 1
-    for nt in sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)}):
+    for nt in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
         torch.set_num_threads(nt)
-        torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
+        for _ in range(2):
+            torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(4):
             torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
         dt = time.perf_counter() - t0
-        if best is None or dt < best:
+        if best is None or dt < best * 0.95:       # prefer fewer threads unless clearly faster
             best, cores = dt, nt
     torch.set_num_threads(cores)
-    sd = unet_ref.make_synthetic_state_dict(LARGE_CFG, seed=1234)
+    return cores
+
+
+def cpu_reference(config, steps, warmup, budget_s):
+    """Times the CPU oracle port on a bounded sample of the workload: `steps` denoising steps of each network at batch 1
+    (after >= `warmup` warm steps, at least one), plus — configs 3/4 — one CPU warp (mesh build + software rasteriser +
+    aggregate_conditions) per distinct source count.  Returns (samples_per_s, description dict)."""
+    from oracle import sampler_ref, unet_ref
+    wl = WORKLOADS[config]
+    cores = pick_threads()
     tb = sampler_ref.Tables(sampler_ref.get_betas("linear", 1000))
-    model = lambda x, t, c: unet_ref.unet_forward(LARGE_CFG, sd, x, t, c)
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 4, 128, 128, generator=g)
-    classes = torch.tensor([7])
+    phases = [k for k in ("uncond", "cond") if wl[k]]
+    per_phase_budget = budget_s * (0.85 if wl["views"] == 1 else 0.7) / len(phases)
+    times, counts = {}, {}
+    for ph in phases:
+        key = wl[ph]
+        cfg = MODELS[key]
+        sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234 if ph == "uncond" else 4321)
+        model = lambda x, t, c: unet_ref.unet_forward(cfg, sd, x, t, c)
+        S = cfg["image_size"]
+        x = torch.randn(1, 4, S, S, generator=g)
+        classes = torch.tensor([7])
+        if key == "Lc":
+            y = torch.randn(1, 4, S, S, generator=g); m = (torch.rand(1, 1, S, S, generator=g) > 0.3).float()
+        elif key == "SR":
+            y = torch.randn(1, 4, S // 2, S // 2, generator=g)
+        state = {"x": x}
 
-    def one(i):
-        nonlocal x
-        t = torch.tensor([999 - i])
-        eps = sampler_ref.cfg_eps(model, x, t, classes, GUIDANCE)
-        x, _ = sampler_ref.ddpm_step(tb, x, t, eps, torch.randn(x.shape, generator=g))
+        def one(i):
+            xx = state["x"]
+            if key == "L":
+                t = torch.tensor([999 - i])
+                eps = sampler_ref.cfg_eps(model, xx, t, classes, GUIDANCE)
+                state["x"], _ = sampler_ref.ddpm_step(tb, xx, t, eps, torch.randn(xx.shape, generator=g))
+                return
+            t = torch.tensor([1000 - 20 * i]); tp = t - 20
+            if key == "Lc":
+                z = torch.randn(1, 4, S, S, generator=g)
+                inp = sampler_ref.make_inpaint_inputs(xx, y, m, m, z[:, :3], z[:, 3:])
+                eps = sampler_ref.cond_eps(model, inp, t - 1, classes, GUIDANCE)
+                state["x"], _ = sampler_ref.ddim_step(tb, xx, t, tp, eps, torch.zeros_like(xx), replace_rgb=(0.1, y[:, :3], m),
+                                                      replace_depth=(0.2, y[:, 3:], m), constrain_depth=(0.5, y[:, 3:]))
+            else:
+                eps = sampler_ref.cond_eps(model, sampler_ref.make_sr_inputs(xx, y), t - 1, classes, GUIDANCE)
+                state["x"], _ = sampler_ref.ddim_step(tb, xx, t, tp, eps, torch.zeros_like(xx))
 
-    t0 = time.perf_counter(); one(0); first = time.perf_counter() - t0
-    # bound the sample: fit warmup + steps into the budget
-    n_warm = max(0, min(warmup, int(budget_s * 0.2 / max(first, 1e-3)) - 1))
-    for i in range(n_warm):
-        one(1 + i)
-    n = max(1, min(steps, int(budget_s * 0.7 / max(first, 1e-3))))
-    t0 = time.perf_counter()
-    for i in range(n):
-        one(1 + n_warm + i)
-    dt = (time.perf_counter() - t0) / n
-    return dt, n, cores
+        t0 = time.perf_counter(); one(0); first = time.perf_counter() - t0          # cold step: never timed
+        n_warm = max(1, min(warmup, int(per_phase_budget * 0.25 / max(first, 1e-3))))
+        for i in range(n_warm):
+            one(1 + i)
+        n = max(1, min(steps, int(per_phase_budget * 0.6 / max(first, 1e-3))))
+        t0 = time.perf_counter()
+        for i in range(n):
+            one(1 + n_warm + i)
+        times[ph] = (time.perf_counter() - t0) / n
+        counts[ph] = n
+        del sd
+    t_warp = 0.0
+    warp_note = ""
+    if wl["views"] > 1:
+        from oracle import warp_ref
+        rng = np.random.default_rng(0)
+        views = [warp_ref.view_on_sphere(0.0, 0.0), warp_ref.view_on_sphere(0.15, 0.0)]      # the first two cameras of the view set
+        kw = dict(WARP_KW)
+        rgbd = synth_rgbd(rng)
+        t0 = time.perf_counter()
+        mesh = warp_ref.depth_to_mesh(warp_ref.linearize_depth(rgbd[:, :, 3:], kw["near"], kw["far"]), fov=kw["fov"],
+                                      modelview=np.asarray(views[0], np.float64), atol=kw["atol"], rtol=kw["rtol"], erode_rgb=kw["erode_rgb"])
+        t_mesh = time.perf_counter() - t0
+        rend = warp_ref.SoftwareAggregationRenderer(384, 128)
+        t0 = time.perf_counter()
+        warp_ref.aggregate_conditions(rend, [mesh], [rgbd[:, :, :3]], np.asarray(views[1], np.float64), **kw)
+        t_agg1 = time.perf_counter() - t0
+        # the software renderer rasterises every source view for every target: cost is linear in the source count
+        V = wl["views"]
+        t_warp = V * t_mesh + t_agg1 * sum(range(1, V))
+        warp_note = f"; CPU warp: 1 mesh build ({t_mesh * 1e3:.0f} ms) + 1 aggregate with 1 source ({t_agg1 * 1e3:.0f} ms), scaled linearly to {sum(range(1, V))} source-view rasterisations"
+    sec = seconds_per_batch(wl, times.get("uncond", 0.0), times.get("cond", 0.0), t_warp)      # batch 1
+    desc = {"cores": cores, "kind": "port",
+            "sample": ", ".join(f"{counts[ph]} {wl[ph]} denoising steps (guidance, 2 forwards each)" for ph in phases) +
+                      f" at batch 1, fp32 torch CPU, {cores} threads" + warp_note,
+            "ms_per_step": {ph: times[ph] * 1e3 for ph in phases}}
+    return 1.0 / sec, desc
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    dt, n, cores = cpu_step_seconds(args.steps, args.warmup)
-    value = 1.0 / (DENOISE_STEPS * dt)
+    value, desc = cpu_reference(args.config, args.steps, max(args.warmup, 1), budget_s=150.0)
+    wl = WORKLOADS[args.config]
     line = {
         "impl": "reference", "metric": "128x128 RGBD multiview samples/sec", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "rgbd_imagenet_adm_128_large_cfg uncond, DDPM 1000 steps + CFG(0.5), CPU oracle port of the reference path",
-                   "batch": 1, "denoise_steps_per_sample": DENOISE_STEPS, "timed_unit": "one denoising step (2 UNet forwards)"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} DDPM+CFG denoising steps at batch 1 (fp32, torch CPU, {cores} threads)"},
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(desc["ms_per_step"].values()),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"] + " — CPU oracle port of the reference path", "batch": 1,
+                   "denoise_steps_per_sample": DENOISE_STEPS if wl["uncond"] else COND_STEPS,
+                   "timed_unit": "one denoising step of each network (2 UNet forwards each)", "phase_ms": desc["ms_per_step"]},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": desc["cores"], "kind": "port", "sample": desc["sample"]},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -161,26 +269,27 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def _ncu_traffic():
-    """DRAM bytes per launch of the dominant conv kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    """DRAM bytes of ONE named launch of the dominant conv kernel (the 128x128 256->256 conv with fp32 + fp16 outputs and
+    residual) from the committed `ncu --set full` capture, or (None, None)."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*_conv_summary.json")))
     if not files:
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot, n = 0.0, 0
+    best = None
     for k in json.load(open(files[-1])):
         try:
             b = 0.0
             for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 v, u = k[key].split()
                 b += float(v.replace(",", "")) * unit[u]
-            tot += b
-            n += 1
+            if best is None or b > best:
+                best = b           # the residual conv (conv2) is the larger of the two captured launches
         except (KeyError, ValueError):
             continue
-    if n == 0:
+    if best is None:
         return None, None
-    return tot / n, f"{os.path.relpath(files[-1], ROOT)}: mean of {n} captured conv_gemm launches (conv1 / conv2 of the first 128x128 ResBlock)"
+    return best, f"{os.path.relpath(files[-1], ROOT)}: the 128x128 256->256 conv2 launch (fp32 + fp16 outputs + fp32 residual; algorithmic 1.61 GB)"
 
 
 def main():
@@ -189,17 +298,28 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="samples per GPU (BASELINE configs[1]: 16)")
-    ap.add_argument("--full", action="store_true", help="one bench step = a complete 1000-step sample batch")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the configuration's, 16 / 8)")
+    ap.add_argument("--full", action="store_true", help="one bench step = a complete sample batch (all steps, all views)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3) if not args.full else args.warmup
+    wl = WORKLOADS[args.config]
+    B = args.batch or wl["batch"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only): same procedure as the reference arm, before this process touches the GPU, so the
+    # thread probe and the warm-up steps see an idle host
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, desc = cpu_reference(args.config, 3, 2, budget_s=45.0)
+        cpu = {"value": v, "unit": "samples/s", "cores": desc["cores"], "kind": "port", "sample": desc["sample"]}
+
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -213,41 +333,88 @@ def main():
     import ivid_b200.backbones as backbones
     import ivid_b200.frameworks as frameworks
     import ivid_b200.samplers as samplers
+    from ivid_b200.inference.sample import build_modelviews, sample_all
+    from ivid_b200.rgbd_3d import DeviceWarp
     from oracle import unet_ref   # only for the synthetic weight generator + cpu_baseline leg
 
-    net = backbones.AdmUnet2d(**LARGE_CFG)
-    if rank == 0:
-        net.load_state_dict(unet_ref.make_synthetic_state_dict(LARGE_CFG, seed=1234))
-    net = net.cuda()
-    net.repack()
-    bcast_ms = None
-    if world > 1:
-        # weights: packed on rank 0, ONE NCCL broadcast of the device arena over NVLink (sample.py:186-195 loads per rank)
-        ptr, nbytes = net.weight_arena()
+    bcast_ms = []
 
-        class _Arena:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        arena = torch.as_tensor(_Arena(), device=dev)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.broadcast(arena, src=0); e1.record(); torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-    fw = frameworks.ClassifierFreeGuidance(net, timesteps=1000, beta_schedule="linear", p_uncond=0.1)
-    sampler = samplers.DdpmSampler(fw)
+    def make_net(key, seed):
+        cfg = MODELS[key]
+        net = backbones.AdmUnet2d(**cfg)
+        if rank == 0:
+            net.load_state_dict(unet_ref.make_synthetic_state_dict(cfg, seed=seed))
+        net = net.cuda()
+        net.repack()
+        if world > 1:
+            # weights: packed on rank 0, ONE NCCL broadcast of the device arena over NVLink (sample.py:186-195 loads per rank)
+            ptr, nbytes = net.weight_arena()
 
-    B = args.batch
+            class _Arena:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            arena = torch.as_tensor(_Arena(), device=dev)
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dist.broadcast(arena, src=0); e1.record(); torch.cuda.synchronize()
+            bcast_ms.append(e0.elapsed_time(e1))
+        return net
+
     gen = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.randn(B, 4, 128, 128, generator=gen).pin_memory()
     classes_host = (torch.arange(B) + rank * B) % 1000
-    x = x_host.to(dev)
     classes = classes_host.to(dev)
+    fw_u = fw_c = s_u = s_c = None
+    if wl["uncond"]:
+        fw_u = frameworks.ClassifierFreeGuidance(make_net(wl["uncond"], 1234), timesteps=1000, beta_schedule="linear", p_uncond=0.1)
+        s_u = samplers.DdpmSampler(fw_u)
+    if wl["cond"] == "Lc":
+        fw_c = frameworks.InpaintCFG(make_net("Lc", 4321), timesteps=1000, beta_schedule="linear")
+        s_c = samplers.DdimSampler(fw_c)
+    elif wl["cond"] == "SR":
+        fw_c = frameworks.SuperResCFG(make_net("SR", 4321), timesteps=1000, beta_schedule="linear")
+        s_c = samplers.DdimSampler(fw_c)
+    S = MODELS[wl["uncond"] or wl["cond"]]["image_size"]
+    x_host = torch.randn(B, 4, S, S, generator=gen).pin_memory()
+    x = x_host.to(dev)
+
+    # conditional-model inputs: the condition maps of a real warp of synthetic source views (configs 3/4), low-res RGBD (5)
+    rng = np.random.default_rng(7 + rank)
+    cond_kw, cond_host = {}, {}
+    warp = None
+    views = build_modelviews("3x9", 1) if wl["views"] > 1 else None
+    src = None
+    if wl["cond"] == "Lc":
+        src = torch.from_numpy(np.stack([synth_rgbd(rng).transpose(2, 0, 1) * 2 - 1 for _ in range(B)])).float().to(dev)
+        warp = DeviceWarp(B, image_size=128, ssaa=3, max_views=max(wl["views"], 2), device=local)
+        warp.add_view(src, views[0], **WARP_KW)
+        c7 = warp.aggregate(views[1], **WARP_KW)
+        y = (c7[:, 0:4] * 2 - 1).contiguous(); m = c7[:, 4:5].contiguous(); mr = c7[:, 5:6].contiguous(); cv = (c7[:, 6:7] * 2 - 1).contiguous()
+        cond_kw = dict(y=y, mask=m, mask_rgb=mr, replace_rgb=(0.1, y[:, :3].contiguous(), mr), replace_depth=(0.2, y[:, 3:].contiguous(), m),
+                       constrain_depth=(0.5, cv))
+        cond_host = {k: v.cpu().pin_memory() for k, v in dict(y=y, mask=m, mask_rgb=mr, convex=cv).items()}
+    elif wl["cond"] == "SR":
+        y = torch.randn(B, 4, S // 2, S // 2, generator=gen).to(dev)
+        cond_kw = dict(y=y)
+        cond_host = {"y": y.cpu().pin_memory()}
     kw = {"strength": GUIDANCE}
 
-    def dstep(xc, i):
-        return sampler._native_step(xc, (DENOISE_STEPS - 1 - i) % DENOISE_STEPS, 0, classes, False, 0.0, kw, None, None).pred_x_prev
+    def step_u(xc, i):
+        return s_u._native_step(xc, (DENOISE_STEPS - 1 - i) % DENOISE_STEPS, 0, classes, False, 0.0, kw, None, None).pred_x_prev
 
-    def full_sample():
-        return sampler.sample(B, noise=x, classes=classes, strength=GUIDANCE, verbose=False).samples
+    def step_c(xc, i):
+        k = i % COND_STEPS
+        return s_c._native_step(xc, 1000 - 20 * k, 980 - 20 * k, classes, False, 0.0, dict(kw, **cond_kw), None, None).pred_x_prev
+
+    def full_batch():
+        if args.config == 2:
+            return s_u.sample(B, noise=x, classes=classes, strength=GUIDANCE, verbose=False).samples
+        if args.config == 5:
+            return s_c.sample(B, noise=x, classes=classes, steps=COND_STEPS, strength=GUIDANCE, verbose=False, **cond_kw).samples
+        mvs = build_modelviews("random", B, rng=np.random.default_rng(3)) if args.config == 3 else views
+        out = None
+        for out in sample_all(fw_u, fw_c, B, DENOISE_STEPS, COND_STEPS, mvs, classes=[int(c) for c in classes_host], guidance=GUIDANCE,
+                              batchsize=B, **WARP_KW):
+            pass
+        return out[2]
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,79 +422,141 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ev = lambda: torch.cuda.Event(enable_timing=True)
     # ---- warm-up ----
-    xc = x
+    xu = xc = x
     for i in range(args.warmup):
-        xc = full_sample() if args.full else dstep(xc, i)
-    # ---- timed region ----
+        if args.full:
+            xu = full_batch()
+        else:
+            if s_u: xu = step_u(xu, i)
+            if s_c: xc = step_c(xc, i)
+    # ---- timed region: K steps ----
     clocks = ClockSampler(local) if rank == 0 else None
     barrier()
     if clocks:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
+    marks = []
     e0.record()
     for i in range(args.steps):
-        xc = full_sample() if args.full else dstep(xc, args.warmup + i)
+        if args.full:
+            xu = full_batch()
+            continue
+        a = ev(); a.record()
+        if s_u: xu = step_u(xu, args.warmup + i)
+        b = ev(); b.record()
+        if s_c: xc = step_c(xc, args.warmup + i)
+        c = ev(); c.record()
+        marks.append((a, b, c))
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop() if clocks else None
-    if dist is not None:
-        tt = torch.tensor([ms_total], device=dev)
+    t_u = sum(a.elapsed_time(b) for a, b, _ in marks) / max(len(marks), 1) / 1e3
+    t_c = sum(b.elapsed_time(c) for _, b, c in marks) / max(len(marks), 1) / 1e3
+    finite = bool(torch.isfinite(xu).all() and torch.isfinite(xc).all())
+
+    # ---- the warp sequence of the view set (device time, CUDA events; configs 3/4, not under --full) ----
+    t_warp, warp_info = 0.0, None
+    if warp is not None and not args.full:
+        V = wl["views"]
+        reps = 2
+        agg_ms, add_ms = [], []
+        for rep in range(reps + 1):                      # first repetition = warm-up
+            warp.reset()
+            a_tot = d_tot = 0.0
+            for j in range(V):
+                if j > 0:
+                    a, b = ev(), ev(); a.record(); c7 = warp.aggregate(views[j], **WARP_KW); b.record(); torch.cuda.synchronize()
+                    a_tot += a.elapsed_time(b)
+                a, b = ev(), ev(); a.record(); warp.add_view(src, views[j], **WARP_KW); b.record(); torch.cuda.synchronize()
+                d_tot += a.elapsed_time(b)
+            if rep > 0:
+                agg_ms.append(a_tot); add_ms.append(d_tot)
+        t_warp = (min(agg_ms) + min(add_ms)) / 1e3
+        # algorithmic bytes: per (sample, target) with j sources: j*(4*128^2*4 + 384^2*8*2) + 7*128^2*4
+        alg = sum(B * (j * (4 * 128 * 128 * 4 + 384 * 384 * 16) + 7 * 128 * 128 * 4) for j in range(1, V))
+        warp_info = {"aggregate_ms_total": min(agg_ms), "add_view_ms_total": min(add_ms), "source_view_rasterisations": B * sum(range(1, V)),
+                     "algorithmic_GB": alg / 1e9, "achieved_GBs": alg / 1e9 / (min(agg_ms) / 1e3),
+                     "frac_of_hbm_peak": alg / 1e9 / (min(agg_ms) / 1e3) / _peaks()["hbm"], "mask_coverage_last_view": float(c7[:, 4].mean())}
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        tt = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
+        return float(tt.item())
+    ms_total, t_u, t_c, t_warp = reduce_max(ms_total), reduce_max(t_u), reduce_max(t_c), reduce_max(t_warp)
     ms_per_step = ms_total / args.steps
-    finite = bool(torch.isfinite(xc).all())
     if args.full:
         value = world * B / (ms_per_step / 1e3)
     else:
-        value = world * B / (DENOISE_STEPS * ms_per_step / 1e3)
+        value = world * B / seconds_per_batch(wl, t_u, t_c, t_warp)
 
     # ---- e2e: the public API call a user makes, host buffers, H2D + D2H inside the timed region ----
-    out_host = torch.empty(B, 4, 128, 128).pin_memory()
+    out_host = torch.empty(B, 4, S, S).pin_memory()
     t_host = torch.full((B,), 500, dtype=torch.int64)
 
-    def e2e_step(i):
-        xd = x_host.to(dev, non_blocking=True)
-        cd = classes_host.to(dev, non_blocking=True)
+    def to_dev(d):
+        return {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+
+    def e2e_u():
+        r = s_u.sample_once(x_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True), classes_host.to(dev, non_blocking=True),
+                            strength=GUIDANCE)
+        out_host.copy_(r.pred_x_prev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def e2e_c():
+        xd = x_host.to(dev, non_blocking=True); cd = classes_host.to(dev, non_blocking=True)
         td = t_host.to(dev, non_blocking=True)
-        r = sampler.sample_once(xd, td, cd, strength=GUIDANCE)
+        h = to_dev(cond_host)
+        if wl["cond"] == "Lc":
+            r = s_c.sample_once(xd, td, td - 20, cd, strength=GUIDANCE, y=h["y"], mask=h["mask"], mask_rgb=h["mask_rgb"],
+                                replace_rgb=(0.1, h["y"][:, :3], h["mask_rgb"]), replace_depth=(0.2, h["y"][:, 3:], h["mask"]),
+                                constrain_depth=(0.5, h["convex"]))
+        else:
+            r = s_c.sample_once(xd, td, td - 20, cd, strength=GUIDANCE, y=h["y"])
         out_host.copy_(r.pred_x_prev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     if args.full:
-        def e2e_step(i):  # noqa: F811
-            r = sampler.sample(B, noise=x_host.to(dev, non_blocking=True), classes=classes_host.to(dev, non_blocking=True),
-                               strength=GUIDANCE, verbose=False)
-            out_host.copy_(r.samples, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    for i in range(2 if not args.full else 0):
-        e2e_step(i)
-    barrier()
-    n_e2e = args.steps
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        e2e_step(i)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    if dist is not None:
-        tt = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    e2e_value = world * B / e2e_s if args.full else world * B / (DENOISE_STEPS * e2e_s)
-    h2d = x_host.numel() * 4 + classes_host.numel() * 8 + (0 if args.full else t_host.numel() * 8)
-    d2h = out_host.numel() * 4
+        e2e_value, h2d, d2h = value, x_host.numel() * 4 + classes_host.numel() * 8, out_host.numel() * 4
+        e2e_api = "same run: DdpmSampler / DdimSampler.sample (sample_all for the multiview configurations) from host noise, samples read back"
+    else:
+        for _ in range(2):
+            if s_u: e2e_u()
+            if s_c: e2e_c()
+        barrier()
+        tu = tc = 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            if s_u: e2e_u()
+            t1 = time.perf_counter()
+            if s_c: e2e_c()
+            t2 = time.perf_counter()
+            tu += t1 - t0; tc += t2 - t1
+        barrier()
+        tu, tc = reduce_max(tu / args.steps), reduce_max(tc / args.steps)
+        e2e_value = world * B / seconds_per_batch(wl, tu, tc, t_warp)
+        nb = lambda t: t.numel() * t.element_size()
+        h2d = (nb(x_host) + nb(classes_host) + nb(t_host)) * (int(bool(s_u)) + int(bool(s_c))) + sum(nb(v) for v in cond_host.values())
+        d2h = nb(out_host) * (int(bool(s_u)) + int(bool(s_c)))
+        e2e_api = "Ddpm/DdimSampler.sample_once(x_t, t[, t_prev], classes, strength[, y, mask, ...]) from pinned host tensors, x_{t-1} read back to host"
 
     # ---- roofline of the dominant kernel (per-launch CUDA events inside the library, one profiled step) ----
     L = _lib.lib()
-    _lib.check(L.ivid_unet_profile_begin(net._handle))
-    dstep(x, 1)
+    net_p = (fw_u or fw_c).backbone
+    key_p = wl["uncond"] or wl["cond"]
+    _lib.check(L.ivid_unet_profile_begin(net_p._handle))
+    (step_u if s_u else step_c)(x, 1)
     buf = ctypes.create_string_buffer(1 << 19)
-    _lib.check(L.ivid_unet_profile_end(net._handle, buf, len(buf)))
+    _lib.check(L.ivid_unet_profile_end(net_p._handle, buf, len(buf)))
     prof = json.loads(buf.value.decode())
     per_op = prof.pop("_ops", None)
     if per_op is not None and rank == 0:
-        with open(os.path.join(ROOT, "gpurun_out", "per_op_profile.json"), "w") as f:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"per_op_profile_c{args.config}.json"), "w") as f:
             json.dump(per_op, f)
     peaks = _peaks()
     dom = max((k for k in prof if k.startswith("conv_gemm")), key=lambda k: prof[k]["ms"])
@@ -336,43 +565,51 @@ def main():
     step_ms_prof = sum(v["ms"] for v in prof.values())
     traffic, traffic_src = _ncu_traffic()
     roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_unit": "DRAM bytes/launch", "traffic_source": traffic_src,
-                "peak_source": peaks["src"] + ", bf16/fp16 dense sustained",
+                "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_unit": "DRAM bytes of the named launch", "traffic_source": traffic_src,
+                "peak_source": peaks["src"] + ", bf16/fp16 dense sustained", "model": key_p,
                 "launches_per_step": d["launches"], "kernel_share_of_step": d["ms"] / step_ms_prof,
                 "families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
                                  "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()}}
-    launches_per_step = sum(v["launches"] for v in prof.values()) + 3 + 3   # embed op = 4 kernels; + set_step, classes, step
+    if warp_info:
+        roofline["warp"] = dict(warp_info, bound="hbm", peak=peaks["hbm"], unit="GB/s")
+    kernels_per_forward = sum(v["launches"] for v in prof.values()) + 3       # "embed" ops = 3 + 2 kernels
+    # one step = (memset + kernels) replayed as ONE CUDA graph + set_step + class fill + fused step kernel
+    launches_per_step = (kernels_per_forward + 3) * (int(bool(s_u)) + int(bool(s_c)))
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        dt, n, cores = cpu_step_seconds(3, 0, budget_s=40.0)
-        cpu = {"value": 1.0 / (DENOISE_STEPS * dt), "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"{n} DDPM+CFG denoising steps at batch 1 (CPU oracle port of the reference path, fp32, {cores} threads)"}
-
+    nets = [k for k in (wl["uncond"], wl["cond"]) if k]
+    model_tf = None
+    if not args.full:
+        fl = 0.0
+        if s_u: fl += 2 * B * GFLOP_PER_FORWARD[wl["uncond"]] / 1e3
+        if s_c: fl += 2 * B * GFLOP_PER_FORWARD[wl["cond"]] / 1e3
+        model_tf = fl / (t_u + t_c)
     line = {
         "metric": "128x128 RGBD multiview samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16 tensor-core operands, fp32 accumulate / residual stream / GroupNorm / softmax / sampler",
         "data": "synthetic",
-        "config": {"workload": "rgbd_imagenet_adm_128_large_cfg uncond, DDPM 1000 steps + classifier-free guidance 0.5 (BASELINE configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "denoise_steps_per_sample": DENOISE_STEPS,
-                   "timed_unit": "complete 1000-step sample batch" if args.full else "one denoising step of the batch (batch-2N UNet forward + fused CFG/DDPM update)",
-                   "unet_step_ms": None if args.full else ms_per_step,
-                   "model_tflops_per_s": (2 * B * GFLOP_PER_FORWARD / 1e3) / (ms_per_step / 1e3) if not args.full else None,
+        "config": {"workload": wl["name"], "config_id": args.config, "models": nets,
+                   "batch_per_gpu": B, "global_batch": B * world, "views_per_sample": wl["views"],
+                   "denoise_steps_per_sample": {"uncond": DENOISE_STEPS if s_u else 0, "cond_per_view": COND_STEPS if s_c else 0},
+                   "timed_unit": "complete sample batch (all steps, all views)" if args.full else
+                                 "one denoising step of the batch of each network (batch-2N UNet forward + fused guidance mix / x_{t-1} update)",
+                   "composition": None if args.full else "seconds/batch = 1000*t_uncond + (views-1)*50*t_cond + t_warp (module docstring)",
+                   "phase_ms": None if args.full else {"uncond_step": t_u * 1e3, "cond_step": t_c * 1e3, "warp_sequence": t_warp * 1e3},
+                   "unet_step_ms": None if args.full else (t_u or t_c) * 1e3,
+                   "model_tflops_per_s": model_tf,
                    "parallelism": f"dp{world} (samples sharded by batch, no data-path collective)",
                    "l2": "per-step working set (0.84 GB weights + >2 GB activations) exceeds the 126 MB L2; no flush needed",
-                   "weights_broadcast_ms": bcast_ms, "finite": finite},
+                   "weights_broadcast_ms": bcast_ms or None, "finite": finite},
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "DdpmSampler.sample_once(x_t, t, classes, strength) from pinned host tensors, result read back to host"
-                       if not args.full else "DdpmSampler.sample(...) from pinned host noise, samples read back"},
-        "gpu_launches": launches_per_step * args.steps * (DENOISE_STEPS if args.full else 1),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
+        "gpu_launches": launches_per_step * args.steps * ((DENOISE_STEPS if s_u else COND_STEPS) if args.full else 1),
+        "gpu_kernels_per_unet_forward": kernels_per_forward,
         "clocks": clk,
     }
     if cpu:

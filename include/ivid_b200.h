@@ -62,6 +62,11 @@ int ivid_unet_weight_arena(const ivid_unet_t* h, void** dev_ptr, uint64_t* bytes
 int ivid_unet_forward(ivid_unet_t* h, const float* x_dev, int Nx, const int64_t* t_dev, const int64_t* classes_dev,
                       float* eps_dev, int N, void* stream);
 
+/* Parity aid (per-layer taps, tests/test_gpu_unet.py): output of the module `layer` (reference module path such as
+ * "input_blocks.3.0", "middle_block.1", "output_blocks.14.0"; the stem is "input_blocks.0.0") of the LAST forward of batch
+ * N, as fp32 NCHW on the host.  host_out == NULL only queries the shape.  Synchronises the device. */
+int ivid_unet_debug_tap(ivid_unet_t* h, int N, const char* layer, float* host_out, uint64_t capacity, int* C, int* H, int* W);
+
 /* Profiling aid (bench.py roofline): between begin/end every kernel launch of ivid_unet_forward is bracketed by CUDA
  * events on the launching stream; end returns JSON {"kernel family": {"launches","ms","flops","bytes"}} where flops /
  * bytes are the ALGORITHMIC figures of DESIGN.md.  Forwards issued while profiling synchronise the stream. */
@@ -125,6 +130,17 @@ typedef struct {
 int ivid_sampler_step(ivid_sampler_t* s, ivid_unet_t* unet, const float* x_t_dev, float* x_prev_dev,
                       float* pred_x0_dev, int N, int t, int t_prev, const ivid_step_args_t* args, void* stream);
 
+/* Same step with t / t_prev read on the device from element 0 of the caller's [N] int64 tensors (the tensors
+ * sample_once receives, ddpm.py:111, ddim.py:48): no device->host synchronisation.  Steps outside the schedule are
+ * clamped (the host-int entry point above raises instead).  Philox stream = t. */
+int ivid_sampler_step_dev(ivid_sampler_t* s, ivid_unet_t* unet, const float* x_t_dev, float* x_prev_dev,
+                          float* pred_x0_dev, int N, const int64_t* t_dev, const int64_t* t_prev_dev,
+                          const ivid_step_args_t* args, void* stream);
+
+/* ClassifierFreeGuidance.model_inference's mix alone (classifier_free_guidance.py:42): out = (1+s)*eps[0:count) -
+ * s*eps[count:2*count) for the batch-2N forward's output (count = N*C*H*W, multiple of 4). */
+int ivid_cfg_mix(const float* eps2n_dev, float strength, float* out_dev, uint64_t count, void* stream);
+
 /* sample: the whole reverse process on device (ddpm.py:134-187, ddim.py:106-165); x_inout_dev holds x_T on entry
  * and the samples on return.  `steps` = DDIM step count (ignored for DDPM, which runs all T).  Optional
  * noise_all_dev [steps][N,C,H,W] / cond_noise_all_dev [steps][N,4,H,W] inject the per-step draws; traj_x0_dev /
@@ -146,8 +162,8 @@ typedef struct {
   double fov_deg;   /* sample.py:258 --fov 45 */
   double near;      /* sample.py:259 --near 0.6  (z-buffer depth <-> linear depth) */
   double far;       /* sample.py:260 --far 5 */
-  double atol;      /* sample.py:261 */
-  double rtol;      /* sample.py:262 */
+  double atol;      /* sample.py:261; negative = Python's None.  depth_to_mesh (utils.py:227-229): both None -> no discontinuity test, */
+  double rtol;      /* sample.py:262;   exactly one None -> that tolerance is 0.  Other entry points take a negative value as 0.      */
   int erode_rgb;    /* sample.py:263 */
   double padding;   /* depth_to_mesh padding: 0 = 'frustum' (sample.py:131: ring pushed out one pixel and pulled to z = -0.1);
                        > 0 = that many pixels, ring not pulled (inference/utils.py:107 load_scene uses 32 for free-view rendering) */

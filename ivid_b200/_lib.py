@@ -73,12 +73,15 @@ SIGNATURES = {
     "ivid_unet_weight_arena": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64)]),
     "ivid_unet_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ivid_unet_forward_cond": (c_int, [c_void_p, c_void_p, c_int, POINTER(CondT), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ivid_unet_debug_tap": (c_int, [c_void_p, c_int, c_char_p, c_void_p, c_uint64, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "ivid_unet_profile_begin": (c_int, [c_void_p]),
     "ivid_unet_profile_end": (c_int, [c_void_p, c_char_p, c_int]),
     "ivid_sampler_create": (c_int, [POINTER(c_double), c_int, POINTER(c_void_p)]),
     "ivid_sampler_destroy": (c_int, [c_void_p]),
     "ivid_sampler_table": (c_int, [c_void_p, c_int, POINTER(c_double), c_int]),
     "ivid_sampler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(StepArgsT), c_void_p]),
+    "ivid_sampler_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(StepArgsT), c_void_p]),
+    "ivid_cfg_mix": (c_int, [c_void_p, c_float, c_void_p, c_uint64, c_void_p]),
     "ivid_sampler_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(StepArgsT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ivid_op_conv2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

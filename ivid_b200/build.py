@@ -42,6 +42,7 @@ def _digest(paths) -> str:
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(EXTRA_FLAGS.items())).encode())
     return h.hexdigest()
 
 

@@ -116,6 +116,13 @@ int ivid_unet_forward_cond(ivid_unet_t* h, const float* x_dev, int Nx, const ivi
   });
 }
 
+int ivid_unet_debug_tap(ivid_unet_t* h, int N, const char* layer, float* host_out, uint64_t capacity, int* C, int* H, int* W) {
+  return guarded([&] {
+    IVID_NOT_NULL(h); IVID_NOT_NULL(layer);
+    h->impl->debug_tap(N, layer, host_out, static_cast<size_t>(capacity), C, H, W);
+  });
+}
+
 int ivid_unet_profile_begin(ivid_unet_t* h) {
   return guarded([&] { IVID_NOT_NULL(h); h->impl->profile_begin(); });
 }
@@ -152,6 +159,20 @@ int ivid_sampler_step(ivid_sampler_t* s, ivid_unet_t* unet, const float* x_t_dev
   return guarded([&] {
     IVID_NOT_NULL(s); IVID_NOT_NULL(unet); IVID_NOT_NULL(x_t_dev); IVID_NOT_NULL(x_prev_dev); IVID_NOT_NULL(args);
     s->impl->step(*unet->impl, x_t_dev, x_prev_dev, pred_x0_dev, N, t, t_prev, *args, t, static_cast<cudaStream_t>(stream));
+  });
+}
+int ivid_sampler_step_dev(ivid_sampler_t* s, ivid_unet_t* unet, const float* x_t_dev, float* x_prev_dev, float* pred_x0_dev,
+                          int N, const int64_t* t_dev, const int64_t* t_prev_dev, const ivid_step_args_t* args, void* stream) {
+  return guarded([&] {
+    IVID_NOT_NULL(s); IVID_NOT_NULL(unet); IVID_NOT_NULL(x_t_dev); IVID_NOT_NULL(x_prev_dev); IVID_NOT_NULL(args); IVID_NOT_NULL(t_dev);
+    IVID_REQUIRE(args->kind != 1 || t_prev_dev != nullptr, "DDIM step needs t_prev");
+    s->impl->step(*unet->impl, x_t_dev, x_prev_dev, pred_x0_dev, N, 0, 0, *args, 0, static_cast<cudaStream_t>(stream), t_dev, t_prev_dev);
+  });
+}
+int ivid_cfg_mix(const float* eps2n_dev, float strength, float* out_dev, uint64_t count, void* stream) {
+  return guarded([&] {
+    IVID_NOT_NULL(eps2n_dev); IVID_NOT_NULL(out_dev);
+    launch_cfg_mix(eps2n_dev, out_dev, static_cast<size_t>(count), strength, static_cast<cudaStream_t>(stream));
   });
 }
 int ivid_sampler_run(ivid_sampler_t* s, ivid_unet_t* unet, float* x_inout_dev, int N, int steps,

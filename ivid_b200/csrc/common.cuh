@@ -31,6 +31,13 @@ __device__ __forceinline__ bool elect_one_sync() {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// Two-term fp16 split of an fp32 value: segment 0 and 2 carry hi = fp16(v), segment 1 carries lo = fp16(v - hi)
+// (network-input channels of the stem conv, see pack_input_kernel).
+__device__ __forceinline__ __half split_term(float v, int seg) {
+  const __half hi = __float2half_rn(v);
+  return seg == 1 ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

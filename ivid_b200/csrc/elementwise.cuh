@@ -101,6 +101,8 @@ struct GnApplyParams {
   const float* film; int film_ld, film_off;
   int pix_per_block;
   __half* out_act;                      // fp16 [N][Ho][Wo][C]
+  __half* out_lo;                       // optional (same-resolution fp16-source path only): fp16(y - float(fp16(y))), the low half
+                                        // of a two-term split of the activation (operand of the split-precision output conv)
   __half* out_raw16;                    // optional fp16 raw copy (same-resolution only) [N][H][W][C]
   float* out_raw32;                     // optional fp32 raw (resampled) [N][Ho][Wo][C]
 };
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
   }
   auto apply8 = [&](const uint4& rawv, int cg, __half* dst) {
     const __half2* h2 = reinterpret_cast<const __half2*>(&rawv);
-    uint32_t pk[4];
+    uint32_t pk[4], pl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h2[j]);
@@ -422,8 +424,13 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
       }
       if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
       pk[j] = pack_h2(y0, y1);
+      if (p.out_lo != nullptr) {
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&pk[j]));
+        pl[j] = pack_h2(y0 - hi.x, y1 - hi.y);
+      }
     }
     *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + (dst - p.out_act)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   };
   if (kHoist) {
     // division-free addressing: the thread owns channel group cg and every (256 / c8)-th pixel starting at pr
@@ -472,30 +479,77 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
 }
 
 // ----------------------------------------------------------------------------------------------
-// network input: fp32 NCHW [Nx][Cin][H][W] -> fp16 NHWC [N][H][W][64] (zero padded channels); sample n reads n % Nx
-// (lets the two classifier-free-guidance halves share one x without a concat copy).
+// network input: fp32 NCHW [Nx][Cin][H][W] -> fp16 NHWC [N][H][W][64]; sample n reads n % Nx (lets the two
+// classifier-free-guidance halves share one x without a concat copy).
+// The 64 operand channels carry a two-term split of the input, which the stem weights mirror (Unet::finalize):
+//     channels [0,Cin) = hi = fp16(x)      [Cin,2Cin) = lo = fp16(x - hi)      [2Cin,3Cin) = hi      rest 0
+//     weights            Wh                              Wh                                Wl
+// so the stem computes  hi*Wh + lo*Wh + hi*Wl = x*W  to ~2^-21 at no extra cost (K is padded to 64 channels anyway):
+// the input rounding of x_t would otherwise enter every layer coherently.
+// One thread = 8 output channels (16 bytes) of one pixel.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int N,
                                                          int Nx, int Cin, int HW) {
-  const size_t total = static_cast<size_t>(N) * HW;
+  const size_t total = static_cast<size_t>(N) * HW * 8;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(idx / HW);
-    const int p = static_cast<int>(idx % HW);
+    const int g = static_cast<int>(idx & 7);
+    const size_t pixn = idx >> 3;
+    const int n = static_cast<int>(pixn / HW);
+    const int p = static_cast<int>(pixn % HW);
     const float* src = x + (static_cast<size_t>(n % Nx) * Cin) * HW + p;
-    __half* dst = out + idx * 64;
-    uint32_t w[32];
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) w[j] = 0u;
+    for (int k = 0; k < 4; ++k) {
+      __half2 h2;
+      __half e[2];
 #pragma unroll
-    for (int c = 0; c < 16; c += 2) {   // Cin <= 16 (4 / 8 / 10 on this path)
-      const float a = (c < Cin) ? src[static_cast<size_t>(c) * HW] : 0.f;
-      const float b = (c + 1 < Cin) ? src[static_cast<size_t>(c + 1) * HW] : 0.f;
-      w[c >> 1] = pack_h2(a, b);
+      for (int q = 0; q < 2; ++q) {
+        const int oc = g * 8 + 2 * k + q;
+        const int seg = oc / Cin;
+        e[q] = seg < 3 ? split_term(__ldg(src + static_cast<size_t>(oc - seg * Cin) * HW), seg) : __float2half_rn(0.f);
+      }
+      h2 = __halves2half2(e[0], e[1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    *reinterpret_cast<uint4*>(out + pixn * 64 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Output head, second half: eps[n][c][h][w] = bias[c] + sum over the 9 taps of Y[n][h+dy][w+dx][tap*Co + c].
+// The 3x3 output convolution (adm.py:486, Cout = 4) is evaluated as a 1x1 GEMM with 9*Co output columns (one per tap and
+// output channel: every activation element is read once instead of nine times) followed by this shift-and-add; taps that
+// fall outside the image contribute nothing (zero padding).  Y is fp32 NHWC with row pitch ldy.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eps_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                                         float* __restrict__ eps, int N, int H, int W, int Co, int ldy) {
+  const size_t total = static_cast<size_t>(N) * H * W;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % W);
+    const int h = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H));
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    // summation order: tap 0..8 ascending (fixed, so results are bit-reproducible)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const float* src = Y + ((static_cast<size_t>(n) * H + hh) * W + ww) * ldy + tap * Co;
+      if (Co == 4) {
+        const float4 v = ldg_f4(src);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c < Co) acc[c] += __ldg(src + c);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < Co) eps[((static_cast<size_t>(n) * Co + c) * H + h) * W + w] = acc[c] + __ldg(bias + c);
   }
 }
 

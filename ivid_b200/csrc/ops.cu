@@ -297,6 +297,9 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);
   p.out_raw32 = d.out_raw32;
+  p.out_lo = reinterpret_cast<__half*>(d.out_lo);
+  IVID_REQUIRE(d.out_lo == nullptr || (d.mode == 0 && d.x0_half && d.out_raw16 == nullptr && d.out_raw32 == nullptr),
+               "gn_apply: the split (hi/lo) output exists on the same-resolution fp16-source path only");
   const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
   const int Wo = d.mode == 1 ? d.W * 2 : (d.mode == 2 ? d.W / 2 : d.W);
   // One wave of blocks (3 resident per SM) split evenly over the samples, so the statistics -> coefficient prologue is
@@ -327,8 +330,16 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
 
 void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s) {
   IVID_REQUIRE(Cin <= 16, "pack_input: at most 16 input channels");
-  pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,
-                                                                             Cin, HW);
+  IVID_REQUIRE(Cin >= 1 && 3 * Cin <= 64, "pack_input: the two-term split needs 3*Cin <= 64 operand channels");
+  pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW * 8, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,
+                                                                                 Cin, HW);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_eps_gather(const float* Y, const float* bias, float* eps, int N, int H, int W, int Co, int ldy, cudaStream_t s) {
+  IVID_REQUIRE(Co >= 1 && Co <= 7 && 9 * Co <= ldy, "eps_gather: 9*Co tap columns must fit the row pitch");
+  IVID_REQUIRE(Co != 4 || ldy % 4 == 0, "eps_gather: row pitch must keep float4 alignment");
+  eps_gather_kernel<<<ew_grid(static_cast<size_t>(N) * H * W, 256), 256, 0, s>>>(Y, bias, eps, N, H, W, Co, ldy);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 

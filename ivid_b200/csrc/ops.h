@@ -57,8 +57,11 @@ struct GnApplyDesc {
   const float* gamma = nullptr; const float* beta = nullptr;        // [C0 + C1]
   const float* film = nullptr; int film_ld = 0, film_off = 0;       // optional FiLM table (scale | shift)
   void* out_act = nullptr; void* out_raw16 = nullptr; float* out_raw32 = nullptr;
+  void* out_lo = nullptr;      // optional low half of a two-term fp16 split of the output (fp16-source same-resolution path only)
 };
 void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s);
+// eps[n][c][h][w] = bias[c] + sum_tap Y[n][h+dy][w+dx][tap*Co + c]  (output head, see eps_gather_kernel)
+void launch_eps_gather(const float* Y, const float* bias, float* eps, int N, int H, int W, int Co, int ldy, cudaStream_t s);
 void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s);
 
 struct CondPackDesc {
@@ -67,6 +70,7 @@ struct CondPackDesc {
   uint64_t seed = 0; uint32_t stream = 0; const int* stream_dev = nullptr;
 };
 void launch_cond_pack(const CondPackDesc& d, cudaStream_t s);   // sampler.cu
+void launch_cfg_mix(const float* eps2, float* out, size_t count, float strength, cudaStream_t s);   // sampler.cu
 
 void launch_posenc(const int64_t* t, int Nt, const float* freqs, int half, float* out, int N, cudaStream_t s);
 // FiLM table (all ResBlock emb_layers as one product): out = silu(emb) * Wp^T + bias, Wp in the swizzled K-chunk-major

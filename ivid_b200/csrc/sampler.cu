@@ -27,10 +27,36 @@ __global__ void set_step_kernel(StepState* st, int64_t* t_model, int N, int t_in
   for (int i = threadIdx.x; i < N; i += blockDim.x) t_model[i] = t_index;
 }
 
+// same, with the step read from the caller's device tensors (sample_once(x_t, t[, t_prev]) of the reference passes [N]
+// tensors; reading element 0 here removes the device->host sync an int(t[0]) would cost).  Out-of-range steps are
+// clamped into the table (the host path raises instead).
+__global__ void set_step_dev_kernel(StepState* st, int64_t* t_model, int N, const int64_t* t_dev, const int64_t* t_prev_dev,
+                                    int ddim, int T) {
+  long long t = t_dev[0];
+  long long ti = ddim ? t - 1 : t;
+  ti = ti < 0 ? 0 : (ti > T - 1 ? T - 1 : ti);
+  long long tp = (ddim && t_prev_dev != nullptr) ? t_prev_dev[0] : 0;
+  tp = tp < 0 ? 0 : (tp > T ? T : tp);
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->t_index = static_cast<int>(ti);
+    st->t_prev = static_cast<int>(tp);
+    st->stream = static_cast<int>(t);
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) t_model[i] = ti;
+}
+
 __global__ void fill_classes_kernel(const int64_t* classes, int64_t* out, int N) {
   // [classes..., -1 ...]: conditional half then null-class half (classifier_free_guidance.py:39-42)
   for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < 2 * N; i += blockDim.x * gridDim.x)
     out[i] = i < N ? classes[i] : -1;
+}
+
+void launch_cfg_mix(const float* eps2, float* out, size_t count, float strength, cudaStream_t s) {
+  IVID_REQUIRE(count % 4 == 0, "cfg mix: element count must be a multiple of 4");
+  const size_t n4 = count / 4;
+  const int grid = static_cast<int>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));
+  cfg_mix_kernel<<<std::max(grid, 1), 256, 0, s>>>(eps2, out, n4, strength);
+  IVID_CHECK_CUDA(cudaGetLastError());
 }
 
 void launch_cond_pack(const CondPackDesc& d, cudaStream_t s) {
@@ -130,7 +156,8 @@ void Sampler::ensure_device(int N2, size_t eps_elems) {
 }
 
 void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, int N, int t, int t_prev,
-                   const ivid_step_args_t& a, int stream_id, cudaStream_t stream) {
+                   const ivid_step_args_t& a, int stream_id, cudaStream_t stream, const int64_t* t_dev,
+                   const int64_t* t_prev_dev) {
   const UnetConfig& uc = unet.cfg();
   const int C = uc.out_channels, S = uc.image_size, HW = S * S;
   IVID_REQUIRE(N >= 1, "batch must be positive");
@@ -138,18 +165,21 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   const bool ddim = a.kind == 1;
   IVID_REQUIRE(a.kind == 0 || a.kind == 1, "sampler kind must be 0 (DDPM) or 1 (DDIM)");
   const int t_index = ddim ? t - 1 : t;     // ddim.py:81 calls the model with t - 1
-  IVID_REQUIRE(t_index >= 0 && t_index < T_, "t out of range");
-  IVID_REQUIRE(!ddim || (t_prev >= 0 && t_prev <= T_), "t_prev out of range");
+  IVID_REQUIRE(t_dev != nullptr || (t_index >= 0 && t_index < T_), "t out of range");
+  IVID_REQUIRE(t_dev != nullptr || !ddim || (t_prev >= 0 && t_prev <= T_), "t_prev out of range");
   // classifier-free guidance: one batch-2N forward when strength > 0 and the model is class conditional
   const bool has_classes = a.classes_dev != nullptr;
   const bool cfg_two = a.use_cfg && has_classes && a.strength > 0.0f;
   // inpaint_cfg.py:77-78 / sr_cfg.py:53-54: classes None -> single null-class forward, no (1+s) scaling
   const bool scale_only = a.use_cfg && has_classes && !(a.strength > 0.0f);
   const int Nf = cfg_two ? 2 * N : N;
+  IVID_CHECK_CUDA(cudaSetDevice(unet.device()));      // before any allocation: a direct C-ABI caller may be on another device
   ensure_device(Nf, static_cast<size_t>(Nf) * C * HW);
-  IVID_CHECK_CUDA(cudaSetDevice(unet.device()));
 
-  set_step_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<StepState*>(d_state_), d_t_, Nf, t_index, t_prev, stream_id);
+  if (t_dev != nullptr)
+    set_step_dev_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<StepState*>(d_state_), d_t_, Nf, t_dev, t_prev_dev, ddim ? 1 : 0, T_);
+  else
+    set_step_kernel<<<1, 128, 0, stream>>>(reinterpret_cast<StepState*>(d_state_), d_t_, Nf, t_index, t_prev, stream_id);
   IVID_CHECK_CUDA(cudaGetLastError());
   const int64_t* cls = nullptr;
   if (has_classes) {
@@ -162,8 +192,12 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
     }
   }
   ivid_cond_t cond = a.cond;
-  if (cond.kind != 0 && cond.noise_dev == nullptr) { cond.seed = a.seed ^ 0x9E3779B97F4A7C15ull; cond.stream_id = stream_id; }
+  // in-kernel noise of the conditional inputs: Philox(seed', step) with the step read from the device-resident step state
+  // (not passed by value: consecutive steps then replay the same CUDA graph of the forward)
+  if (cond.kind != 0 && cond.noise_dev == nullptr) { cond.seed = a.seed ^ 0x9E3779B97F4A7C15ull; cond.stream_id = 0; }
+  unet.set_cond_stream_dev(cond.kind != 0 && cond.noise_dev == nullptr ? &reinterpret_cast<StepState*>(d_state_)->stream : nullptr);
   unet.forward(x_t, N, cond.kind ? &cond : nullptr, d_t_, cls, d_eps_, Nf, stream);
+  unet.set_cond_stream_dev(nullptr);
 
   StepParams p;
   p.x_t = x_t; p.eps = d_eps_; p.noise = a.step_noise_dev; p.x_prev = x_prev; p.pred_x0 = pred_x0;
@@ -204,6 +238,7 @@ void Sampler::run(Unet& unet, float* x, int N, int steps, const ivid_step_args_t
   if (!ddim) steps = T_;
   IVID_REQUIRE(steps >= 1 && steps <= T_, "steps out of range");
   const int jump = T_ / steps;                     // ddim.py:153
+  IVID_CHECK_CUDA(cudaSetDevice(unet.device()));
   ensure_device(2 * N, 2 * img);
   float* bufs[2] = {x, d_xtmp_};                   // ping-pong; the result is copied back to x if it ends in d_xtmp_
   int cur = 0;

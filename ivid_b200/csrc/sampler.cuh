@@ -87,6 +87,18 @@ __device__ __forceinline__ float mix_eps(const StepParams& p, size_t i, size_t t
   return (1.0f + p.strength) * ec - p.strength * p.eps[total + i];
 }
 
+// classifier-free-guidance mix alone (framework.model_inference): out = (1+s)*eps[0:n) - s*eps[n:2n)
+__global__ void __launch_bounds__(256) cfg_mix_kernel(const float* __restrict__ eps2, float* __restrict__ out, size_t n4, float strength) {
+  const float4* a = reinterpret_cast<const float4*>(eps2);
+  const float4* b = a + n4;
+  float4* o = reinterpret_cast<float4*>(out);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 c = __ldg(a + i), u = __ldg(b + i);
+    o[i] = make_float4((1.0f + strength) * c.x - strength * u.x, (1.0f + strength) * c.y - strength * u.y,
+                       (1.0f + strength) * c.z - strength * u.z, (1.0f + strength) * c.w - strength * u.w);
+  }
+}
+
 // one thread = 4 consecutive pixels of one (n, c) plane
 __global__ void __launch_bounds__(256) ddpm_step_kernel(const StepParams p) {
   const size_t total = static_cast<size_t>(p.N) * p.C * p.HW;
@@ -198,58 +210,82 @@ struct CondPackParams {
 };
 
 __global__ void __launch_bounds__(256) cond_pack_kernel(const CondPackParams p) {
+  // phase 1: one thread per pixel assembles the Cin (<= 16) fp32 input channels into shared memory;
+  // phase 2: the block writes the 64 fp16 operand channels (two-term split hi | lo | hi, see pack_input_kernel) with
+  //          16-byte coalesced stores, one thread per (pixel, 8-channel group).
+  __shared__ float s_ch[256][17];
   const int HW = p.H * p.W;
   const size_t total = static_cast<size_t>(p.N) * HW;
   const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(idx / HW) % p.Nx;
-    const int pix = static_cast<int>(idx % HW);
-    float ch[16];
+  const int Cin = p.kind == 1 ? (p.mask_rgb ? 10 : 9) : 8;
+  for (size_t base = blockIdx.x * static_cast<size_t>(blockDim.x); base < total; base += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t idx = base + threadIdx.x;
+    if (idx < total) {
+      const int n = static_cast<int>(idx / HW) % p.Nx;
+      const int pix = static_cast<int>(idx % HW);
+      float ch[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) ch[j] = 0.f;
+      for (int j = 0; j < 16; ++j) ch[j] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ch[c] = p.x[(static_cast<size_t>(n) * 4 + c) * HW + pix];
-    if (p.kind == 1) {
-      const float m = p.mask[static_cast<size_t>(n) * HW + pix];
-      const float mr = p.mask_rgb ? p.mask_rgb[static_cast<size_t>(n) * HW + pix] : m;
-      float z[4];
-      if (p.noise != nullptr) {
+      for (int c = 0; c < 4; ++c) ch[c] = p.x[(static_cast<size_t>(n) * 4 + c) * HW + pix];
+      if (p.kind == 1) {
+        const float m = p.mask[static_cast<size_t>(n) * HW + pix];
+        const float mr = p.mask_rgb ? p.mask_rgb[static_cast<size_t>(n) * HW + pix] : m;
+        float z[4];
+        if (p.noise != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) z[c] = p.noise[(static_cast<size_t>(n) * 4 + c) * HW + pix];
+          for (int c = 0; c < 4; ++c) z[c] = p.noise[(static_cast<size_t>(n) * 4 + c) * HW + pix];
+        } else {
+          const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(static_cast<size_t>(n) * HW + pix));
+          z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+        }
+        int o = 4;
+        if (p.mask_rgb) ch[o++] = mr;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ch[o++] = p.y[(static_cast<size_t>(n) * 4 + c) * HW + pix] * mr + z[c] * (1.0f - mr);
+        ch[o++] = p.y[(static_cast<size_t>(n) * 4 + 3) * HW + pix] * m + z[3] * (1.0f - m);
+        ch[o++] = m;
       } else {
-        const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(static_cast<size_t>(n) * HW + pix));
-        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-      }
-      int o = 4;
-      if (p.mask_rgb) ch[o++] = mr;
+        // bilinear 2x upsample, align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0 (ATen upsample_bilinear2d)
+        const int h = pix / p.W, w = pix % p.W;
+        const int Hs = p.H / 2, Ws = p.W / 2;
+        float sy = (h + 0.5f) * 0.5f - 0.5f; if (sy < 0.f) sy = 0.f;
+        float sx = (w + 0.5f) * 0.5f - 0.5f; if (sx < 0.f) sx = 0.f;
+        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+        const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+        const float ly = sy - y0, lx = sx - x0;
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        ch[o++] = p.y[(static_cast<size_t>(n) * 4 + c) * HW + pix] * mr + z[c] * (1.0f - mr);
-      ch[o++] = p.y[(static_cast<size_t>(n) * 4 + 3) * HW + pix] * m + z[3] * (1.0f - m);
-      ch[o++] = m;
-    } else {
-      // bilinear 2x upsample, align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0 (ATen upsample_bilinear2d)
-      const int h = pix / p.W, w = pix % p.W;
-      const int Hs = p.H / 2, Ws = p.W / 2;
-      float sy = (h + 0.5f) * 0.5f - 0.5f; if (sy < 0.f) sy = 0.f;
-      float sx = (w + 0.5f) * 0.5f - 0.5f; if (sx < 0.f) sx = 0.f;
-      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-      const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
-      const float ly = sy - y0, lx = sx - x0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float* s = p.y + (static_cast<size_t>(n) * 4 + c) * Hs * Ws;
-        const float v = (1.f - ly) * ((1.f - lx) * s[y0 * Ws + x0] + lx * s[y0 * Ws + x1]) +
-                        ly * ((1.f - lx) * s[y1 * Ws + x0] + lx * s[y1 * Ws + x1]);
-        ch[4 + c] = v;
+        for (int c = 0; c < 4; ++c) {
+          const float* s = p.y + (static_cast<size_t>(n) * 4 + c) * Hs * Ws;
+          const float v = (1.f - ly) * ((1.f - lx) * s[y0 * Ws + x0] + lx * s[y0 * Ws + x1]) +
+                          ly * ((1.f - lx) * s[y1 * Ws + x0] + lx * s[y1 * Ws + x1]);
+          ch[4 + c] = v;
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s_ch[threadIdx.x][j] = ch[j];
     }
-    uint4* d4 = reinterpret_cast<uint4*>(p.out + idx * 64);
-    d4[0] = make_uint4(pack_h2(ch[0], ch[1]), pack_h2(ch[2], ch[3]), pack_h2(ch[4], ch[5]), pack_h2(ch[6], ch[7]));
-    d4[1] = make_uint4(pack_h2(ch[8], ch[9]), pack_h2(ch[10], ch[11]), pack_h2(ch[12], ch[13]), pack_h2(ch[14], ch[15]));
+    __syncthreads();
+    const int live = static_cast<int>(min(static_cast<size_t>(256), total - base));
+    for (int it = threadIdx.x; it < live * 8; it += 256) {
+      const int px = it >> 3, g = it & 7;
+      uint32_t w4[4];
 #pragma unroll
-    for (int j = 2; j < 8; ++j) d4[j] = make_uint4(0u, 0u, 0u, 0u);
+      for (int k = 0; k < 4; ++k) {
+        __half e[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int oc = g * 8 + 2 * k + q;
+          const int seg = oc / Cin;
+          e[q] = seg < 3 ? split_term(s_ch[px][oc - seg * Cin], seg) : __float2half_rn(0.f);
+        }
+        const __half2 h2 = __halves2half2(e[0], e[1]);
+        w4[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(p.out + (base + px) * 64 + g * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+    __syncthreads();
   }
 }
 

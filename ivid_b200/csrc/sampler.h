@@ -14,8 +14,10 @@ class Sampler {
   const std::vector<double>& table(int which) const;
 
   // one reverse step (sample_once).  stream_id = Philox stream for in-kernel noise.
+  // t_dev / t_prev_dev (optional): read the step from element 0 of device tensors instead of the host ints
   void step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, int N, int t, int t_prev,
-            const ivid_step_args_t& a, int stream_id, cudaStream_t stream);
+            const ivid_step_args_t& a, int stream_id, cudaStream_t stream, const int64_t* t_dev = nullptr,
+            const int64_t* t_prev_dev = nullptr);
   // the whole reverse process
   void run(Unet& unet, float* x, int N, int steps, const ivid_step_args_t& a, const float* noise_all,
            const float* cond_noise_all, float* traj_x0, float* traj_xt, cudaStream_t stream);

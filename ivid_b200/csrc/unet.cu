@@ -247,6 +247,35 @@ void pack_conv_rows(__half* dst, int Ktot, int kcol0, const float* w, int cout, 
         dst[static_cast<size_t>(co) * Ktot + kcol0 + tap * cin_pad + ci] =
             __float2half_rn(w[(static_cast<size_t>(co) * cin + ci) * taps + tap]);
 }
+// Stem: the 64 operand channels of the packed network input are  hi | lo | hi  of a two-term fp16 split of x
+// (pack_input_kernel); the matching weight columns are  Wh | Wh | Wl  with W = Wh + Wl, so that the fp16 tensor-core
+// product reproduces x*W to ~2^-21 (the lo*Wl term is dropped).
+void pack_stem_rows(__half* dst, int Ktot, const float* w, int cout, int cin, int cin_pad) {
+  for (int co = 0; co < cout; ++co)
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap];
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        __half* row = dst + static_cast<size_t>(co) * Ktot + tap * cin_pad;
+        row[ci] = hi; row[cin + ci] = hi; row[2 * cin + ci] = lo;
+      }
+}
+
+// Output head as a 1x1 GEMM over 9*Co columns (column tap*Co + c holds W[c][:, tap]), split precision:
+// K = [Wh | Wh | Wl] against the activation segments [a_hi | a_lo | a_hi] (GnApplyParams::out_lo).
+void pack_out_rows(__half* dst, int C, const float* w, int co_n) {
+  const int K = 3 * C;
+  for (int tap = 0; tap < 9; ++tap)
+    for (int c = 0; c < co_n; ++c)
+      for (int ci = 0; ci < C; ++ci) {
+        const float v = w[(static_cast<size_t>(c) * C + ci) * 9 + tap];
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        __half* row = dst + static_cast<size_t>(tap * co_n + c) * K;
+        row[ci] = hi; row[C + ci] = hi; row[2 * C + ci] = lo;
+      }
+}
 }  // namespace
 
 void Unet::finalize(int device) {
@@ -325,6 +354,8 @@ void Unet::finalize(int device) {
     }
   }
   in_conv_ = pack_conv("input_blocks.0.0.weight", "input_blocks.0.0.bias", in_ch_stem_, cfg_.in_channels, 64, 3, "", "", 0);
+  IVID_REQUIRE(3 * cfg_.in_channels <= 64, "in_channels must be <= 21 (two-term input split inside 64 operand channels)");
+  pack_stem_rows(ab.at<__half>(in_conv_.w_off), in_conv_.K, P("input_blocks.0.0.weight").host.data(), in_ch_stem_, cfg_.in_channels, 64);
   for (auto& r : res_) {
     r.gn1 = pack_gn(r.pfx + ".in_layers.0", r.cin);
     r.conv1 = pack_conv(r.pfx + ".in_layers.2.weight", r.pfx + ".in_layers.2.bias", r.cout, r.cin, r.cin, 3, "", "", 0);
@@ -339,6 +370,14 @@ void Unet::finalize(int device) {
   }
   out_gn_ = pack_gn("out.0", final_ch_);
   out_conv_ = pack_conv("out.2.weight", "out.2.bias", cfg_.out_channels, final_ch_, final_ch_, 3, "", "", 0);
+  // split-precision 1x1 form of the same conv (see pack_out_rows); bias is added by eps_gather_kernel
+  out_split_ = 9 * cfg_.out_channels <= 64 && getenv("IVID_NO_OUTSPLIT") == nullptr;
+  if (out_split_) {
+    out1x1_.cout = 64; out1x1_.cout_pad = 64; out1x1_.K = 3 * final_ch_;
+    out1x1_.w_off = ab.alloc(static_cast<size_t>(64) * out1x1_.K * 2);
+    pack_out_rows(ab.at<__half>(out1x1_.w_off), final_ch_, P("out.2.weight").host.data(), cfg_.out_channels);
+    out1x1_.b_off = put_f32(std::vector<float>(64, 0.f));
+  }
 
   arena_bytes_ = (ab.buf.size() + 255) & ~size_t(255);
   IVID_CHECK_CUDA(cudaMalloc(&arena_, arena_bytes_));
@@ -348,6 +387,7 @@ void Unet::finalize(int device) {
 Unet::~Unet() {
   if (side_stream_) { cudaStreamDestroy(side_stream_); cudaEventDestroy(ev_fork_); cudaEventDestroy(ev_join_); }
   plans_.clear();
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (arena_) cudaFree(arena_);
 }
 
@@ -383,7 +423,25 @@ struct Plan {
   const float* x = nullptr; int Nx = 0; ivid_cond_t cond{}; const int64_t* t = nullptr; const int64_t* classes = nullptr;
   float* eps = nullptr;
   const int* cond_stream_dev = nullptr;
+  // CUDA graphs of the whole forward (memset + ~215 launches), one per distinct set of per-call pointers / by-value inputs:
+  // the launch records bake them in, so a replay is valid exactly when the key matches.
+  struct GraphKey {
+    const void* x; int Nx; const void* t; const void* classes; void* eps;
+    int kind; const void* y; const void* mask; const void* mask_rgb; const void* noise; uint64_t seed; uint32_t stream_id;
+    const void* stream_dev;
+    bool operator==(const GraphKey& o) const {
+      return x == o.x && Nx == o.Nx && t == o.t && classes == o.classes && eps == o.eps && kind == o.kind && y == o.y && mask == o.mask &&
+             mask_rgb == o.mask_rgb && noise == o.noise && seed == o.seed && stream_id == o.stream_id && stream_dev == o.stream_dev;
+    }
+  };
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; };
+  // named block outputs (debug taps: per-layer parity tests read them back after a forward)
+  struct Tap { std::string name; const float* d32; const __half* d16; int C, H, W; };
+  std::vector<Tap> taps;
+  std::vector<GraphEntry> graphs;
+  uint64_t runs = 0;
   ~Plan() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     for (auto* c : convs) conv_launch_destroy(c);
     for (auto* a : attns) attn_launch_destroy(a);
     if (ws) cudaFree(ws);
@@ -524,7 +582,7 @@ Plan* Unet::build_plan(int N) {
       return a.data;
     };
     Act pending_stats; bool has_pending_stats = false;
-    auto add_conv = [&](ConvDesc d, const Act* stats_of = nullptr) {
+    auto add_conv = [&](ConvDesc d, const Act* stats_of = nullptr, double k_alg = 0.0, double n_alg = 0.0) {
       // GroupNorm statistics of the output are accumulated in the conv epilogue whenever the tile geometry allows
       const bool fused = stats_of != nullptr && conv_can_fuse_stats(d.H, d.W);
       if (fused) d.stats = stats_of->stats;
@@ -533,12 +591,14 @@ Plan* Unet::build_plan(int N) {
       if (!create) return;
       ConvLaunch* l = conv_launch_create(d);
       pl->convs.push_back(l);
-      const double K = static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0) +
+      // ALGORITHMIC work: operand padding (stem: 9*Cin of 9*64 columns) and split-precision segments do not count
+      const double K = k_alg > 0.0 ? k_alg : static_cast<double>(d.taps0) * d.C0 + (d.C1 > 0 ? static_cast<double>(d.taps1) * d.C1 : 0.0) +
                        (d.C2 > 0 ? static_cast<double>(d.taps2) * d.C2 : 0.0);
       const double M = static_cast<double>(d.N) * d.H * d.W;
+      const double Nalg = n_alg > 0.0 ? n_alg : static_cast<double>(d.cout);
       static const char* names[] = {"conv_gemm<16>", "conv_gemm<64>", "conv_gemm<128>", "conv_gemm<256>"};
       const int bn = conv_launch_bn(l);
-      pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * d.cout,
+      pl->ops.tag(names[bn == 256 ? 3 : bn == 128 ? 2 : bn == 64 ? 1 : 0], 2.0 * M * K * Nalg,
                   M * (d.C0 + d.C1 + d.C2) * 2 + M * d.cout * ((d.out_mode == 1 ? 2 : 4) + (d.out16 ? 2 : 0) + (d.residual ? 4 : 0)) + K * d.cout_pad * 2,
                   std::to_string(d.H) + "x" + std::to_string(d.W) + " " + std::to_string(d.C0) + (d.C1 ? "+" + std::to_string(d.C1) : "") + (d.C2 ? "+" + std::to_string(d.C2) : "") +
                       "->" + std::to_string(d.cout) + " k" + std::to_string(d.taps0) + (d.residual ? " res" : "") + (d.stats ? " stats" : "") +
@@ -625,8 +685,9 @@ Plan* Unet::build_plan(int N) {
       if (only16(cur, false)) { d.out = cur.d16; d.out_mode = 1; }
       else { alloc32(cur); d.out = cur.data; d.out16 = cur.d16; d.out_mode = 0; }
       d.ldc = cur.C; d.N = N; d.H = S; d.W = S;
-      add_conv(d, &cur);
+      add_conv(d, &cur, 9.0 * cfg_.in_channels);
       add_stats(cur);
+      if (create) pl->taps.push_back({"input_blocks.0.0", cur.data, cur.d16, cur.C, cur.H, cur.W});
     }
     std::vector<Act> skips;
     skips.push_back(cur);
@@ -692,6 +753,7 @@ Plan* Unet::build_plan(int N) {
         add_conv(d, &out);
         add_stats(out);
       }
+      if (create) pl->taps.push_back({r.pfx, out.data, out.d16, out.C, out.H, out.W});
       return out;
     };
     auto run_attn = [&](const AttnBlockDef& a, const Act& x) -> Act {
@@ -727,6 +789,7 @@ Plan* Unet::build_plan(int N) {
         add_conv(d, &out);
         add_stats(out);
       }
+      if (create) pl->taps.push_back({a.pfx, out.data, out.d16, out.C, out.H, out.W});
       return out;
     };
 
@@ -754,10 +817,28 @@ Plan* Unet::build_plan(int N) {
     // ---- output head: GN + SiLU + conv3x3 -> eps (fp32 NCHW) ----
     add_coeff(cur, nullptr, out_gn_, -1);
     GnApplyDesc go;
+    const bool split_head = out_split_ && cur.d16 != nullptr;
     if (cur.d16 != nullptr) { go.x0 = cur.d16; go.x0_half = true; } else go.x0 = use32(cur);
     go.C0 = cur.C; go.N = N; go.H = S; go.W = S; go.mode = 0; go.silu = 1; go.out_act = s_a1;
+    if (split_head) go.out_lo = s_a2;
     add_apply(go);
-    if (create) {
+    if (split_head) {
+      // 1x1 GEMM over 9*Co tap columns on [a_hi | a_lo | a_hi] x [Wh | Wh | Wl], then shift-and-add + bias (eps_gather_kernel):
+      // each activation element is read once instead of nine times, and the product carries ~21 mantissa bits
+      ConvDesc d;
+      d.act0 = s_a1; d.C0 = cur.C; d.taps0 = 1;
+      d.act1 = s_a2; d.C1 = cur.C; d.taps1 = 1;
+      d.act2 = s_a1; d.C2 = cur.C; d.taps2 = 1;
+      d.weight = W8(out1x1_.w_off); d.cout_pad = 64; d.cout = 64; d.bias = Wf(out1x1_.b_off);
+      d.out = s_h; d.ldc = 64; d.out_mode = 0; d.N = N; d.H = S; d.W = S;
+      add_conv(d, nullptr, 9.0 * cur.C, static_cast<double>(cfg_.out_channels));
+      if (create) {
+        const float* Y = s_h; const float* ob = Wf(out_conv_.b_off);
+        const int Co = cfg_.out_channels;
+        pl->ops.tag("eps_gather", 0, static_cast<double>(N) * S * S * (9.0 * Co * 4 + Co * 4));
+        pl->ops.push_back([=](cudaStream_t s) { launch_eps_gather(Y, ob, pl->eps, N, S, S, Co, 64, s); });
+      }
+    } else if (create) {
       ConvDesc d;
       d.act0 = s_a1; d.C0 = cur.C; d.taps0 = 9;
       d.weight = W8(out_conv_.w_off); d.cout_pad = out_conv_.cout_pad; d.cout = cfg_.out_channels; d.bias = Wf(out_conv_.b_off);
@@ -846,11 +927,55 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   Plan* pl = get_plan(N, 0);
   pl->x = x; pl->Nx = Nx; pl->t = t; pl->classes = classes; pl->eps = eps;
   pl->cond = cnd;
-  IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
+  pl->cond_stream_dev = cond_stream_dev_;
   if (!profile_) {
+    // The first call of a plan runs eagerly (one-time function attributes, module loading); from the second call on the
+    // forward is ONE cudaGraphLaunch.  Graphs are captured on a private stream (the caller's may be the legacy default
+    // stream, which cannot be captured) and launched on the caller's stream.
+    static const bool graphs_on = getenv("IVID_NO_GRAPH") == nullptr;
+    ++pl->runs;
+    if (graphs_on && pl->runs > 1) {
+      const Plan::GraphKey key{x, Nx, t, classes, eps, cnd.kind, cnd.y_dev, cnd.mask_dev, cnd.mask_rgb_dev, cnd.noise_dev,
+                               cnd.kind != 0 ? cnd.seed : 0ull, cnd.kind != 0 ? cnd.stream_id : 0u, cond_stream_dev_};
+      for (auto& g : pl->graphs)
+        if (g.key == key) {
+          g.last_use = pl->runs;
+          IVID_CHECK_CUDA(cudaGraphLaunch(g.exec, stream));
+          return;
+        }
+      if (cap_stream_ == nullptr) IVID_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      IVID_CHECK_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeRelaxed));
+      try {
+        IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, cap_stream_));
+        for (auto& op : pl->ops.v) op.fn(cap_stream_);
+      } catch (...) {
+        cudaStreamEndCapture(cap_stream_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      IVID_CHECK_CUDA(cudaStreamEndCapture(cap_stream_, &graph));
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      IVID_CHECK_CUDA(ie);
+      if (pl->graphs.size() >= 8) {
+        // evict the least recently used graph; it may still be executing on the caller's stream
+        size_t victim = 0;
+        for (size_t i = 1; i < pl->graphs.size(); ++i) if (pl->graphs[i].last_use < pl->graphs[victim].last_use) victim = i;
+        IVID_CHECK_CUDA(cudaStreamSynchronize(stream));
+        cudaGraphExecDestroy(pl->graphs[victim].exec);
+        pl->graphs.erase(pl->graphs.begin() + victim);
+      }
+      pl->graphs.push_back(Plan::GraphEntry{key, exec, pl->runs});
+      IVID_CHECK_CUDA(cudaGraphLaunch(exec, stream));
+      return;
+    }
+    IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
     for (auto& op : pl->ops.v) op.fn(stream);
     return;
   }
+  IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
   // profiling pass: every launch bracketed by CUDA events on the launching stream (serialised; shares, not absolutes)
   std::vector<cudaEvent_t> ev(pl->ops.v.size() + 1);
   for (auto& e : ev) IVID_CHECK_CUDA(cudaEventCreate(&e));
@@ -874,6 +999,38 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
     }
   }
   for (auto& e : ev) cudaEventDestroy(e);
+}
+
+// Debug tap: output of the named layer (reference module path, e.g. "input_blocks.3.0") of the LAST forward of batch N,
+// converted to fp32 NCHW on the host.  Tensors that only exist as fp16 in the plan (outputs nobody reads in fp32) are
+// widened.  Synchronises the device; not on any hot path.
+void Unet::debug_tap(int N, const std::string& name, float* host_out, size_t capacity, int* C, int* H, int* W) {
+  Plan* pl = nullptr;
+  for (auto& p : plans_) if (p->N == N && p->slot == 0) pl = p.get();
+  if (pl == nullptr) throw Error(kErrState, "debug_tap: no forward of this batch size has run");
+  for (const auto& t : pl->taps) {
+    if (t.name != name) continue;
+    const size_t n = static_cast<size_t>(N) * t.C * t.H * t.W;
+    if (C) *C = t.C; if (H) *H = t.H; if (W) *W = t.W;
+    if (host_out == nullptr) return;
+    IVID_REQUIRE(capacity >= n, "debug_tap: output buffer too small");
+    IVID_CHECK_CUDA(cudaSetDevice(device_));
+    IVID_CHECK_CUDA(cudaDeviceSynchronize());
+    std::vector<float> nhwc(n);
+    if (t.d32 != nullptr) {
+      IVID_CHECK_CUDA(cudaMemcpy(nhwc.data(), t.d32, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<__half> h(n);
+      IVID_CHECK_CUDA(cudaMemcpy(h.data(), t.d16, n * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; ++i) nhwc[i] = __half2float(h[i]);
+    }
+    const size_t HW = static_cast<size_t>(t.H) * t.W;
+    for (int b = 0; b < N; ++b)
+      for (size_t px = 0; px < HW; ++px)
+        for (int c = 0; c < t.C; ++c) host_out[(static_cast<size_t>(b) * t.C + c) * HW + px] = nhwc[(static_cast<size_t>(b) * HW + px) * t.C + c];
+    return;
+  }
+  throw Error(kErrInvalidArgument, "debug_tap: unknown layer '" + name + "'");
 }
 
 void Unet::profile_begin() { profile_ = true; profile_acc_.clear(); profile_ops_.clear(); }

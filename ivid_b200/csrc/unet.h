@@ -80,6 +80,10 @@ class Unet {
   // forward over a batch of N samples; x rows are read modulo Nx (CFG halves share x)
   void forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_t* t, const int64_t* classes, float* eps,
                int N, cudaStream_t stream);
+  // Device-resident Philox stream id (step counter) of the conditional-input noise: the sampler points this at its step
+  // state so that consecutive denoising steps replay the same CUDA graph (a by-value stream id would change the key).
+  void set_cond_stream_dev(const int* p) { cond_stream_dev_ = p; }
+  void debug_tap(int N, const std::string& name, float* host_out, size_t capacity, int* C, int* H, int* W);
   // per-kernel-family timing of the forwards issued between begin/end (CUDA events around every launch)
   void profile_begin();
   std::string profile_end();    // JSON: {"label": {"launches", "ms", "flops", "bytes"}, ...}
@@ -104,6 +108,8 @@ class Unet {
 
   // packed weights
   ConvW in_conv_, out_conv_;
+  ConvW out1x1_;                     // split-precision 1x1 form of the output conv (9*Co tap columns), see unet.cu
+  bool out_split_ = false;
   GnW out_gn_;
   LinW te1_, te2_, film_;
   size_t freqs_off_ = 0, label_off_ = 0;
@@ -111,6 +117,8 @@ class Unet {
   size_t arena_bytes_ = 0;
   int device_ = -1;
 
+  const int* cond_stream_dev_ = nullptr;
+  cudaStream_t cap_stream_ = nullptr;
   cudaStream_t side_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   struct ProfAgg { int launches = 0; double ms = 0, flops = 0, bytes = 0; };

@@ -384,6 +384,7 @@ struct MeshParams {
   double lin0, lin_step;      // np.linspace(0.5/n, 1-0.5/n, n): start, step
   double lin_last;
   float atol_f, rtol_f;
+  int no_disc;                // 1: atol and rtol both None -> mask_discontinuity is skipped entirely (utils.py:227)
   int erode_k;                // 2*erode_rgb+1 (0 = no erosion)
   const float* inv_mv;        // [B][16] row-major float32 inverse(modelview)
   // scratch / outputs
@@ -493,7 +494,7 @@ __global__ void mesh_faces_kernel(const MeshParams p) {
       const float inv = 1.0f / d;
       dmax = fmaxf(dmax, d); dmin = fminf(dmin, d); imax = fmaxf(imax, inv); imin = fminf(imin, inv);
     }
-    if ((dmax - dmin) > p.atol_f && (imax - imin) > p.rtol_f)
+    if (!p.no_disc && (dmax - dmin) > p.atol_f && (imax - imin) > p.rtol_f)
       for (int k = 0; k < 3; ++k) atomicOr(disc + f[t][k], 1);
   }
 }
@@ -805,7 +806,10 @@ class Warp {
     p.step = p.frustum ? (2 * std::tan(0.5 * fov)) / n_ : (wp.padding * (2 * std::tan(0.5 * fov))) / n_;   // utils.py:190,201
     p.lin0 = 0.5 / n_; p.lin_last = 1 - 0.5 / n_;
     p.lin_step = (p.lin_last - p.lin0) / (n_ - 1);
-    p.atol_f = static_cast<float>(wp.atol); p.rtol_f = static_cast<float>(wp.rtol);
+    // a negative tolerance stands for Python's None: both None -> no discontinuity test at all; exactly one None -> that one
+    // is 0 (utils.py:227-229)
+    p.no_disc = (wp.atol < 0.0 && wp.rtol < 0.0) ? 1 : 0;
+    p.atol_f = static_cast<float>(wp.atol < 0.0 ? 0.0 : wp.atol); p.rtol_f = static_cast<float>(wp.rtol < 0.0 ? 0.0 : wp.rtol);
     p.erode_k = wp.erode_rgb > 0 ? 2 * wp.erode_rgb + 1 : 0;
     p.inv_mv = inv_dev_;
     p.pts = pts_; p.nrm = nrm_; p.dep = dep_; p.disc = disc_;
@@ -905,7 +909,8 @@ class Warp {
     p.near_f = static_cast<float>(wp.near); p.far_f = static_cast<float>(wp.far);
     p.inv_near_f = static_cast<float>(1.0 / wp.near);
     p.denom_f = static_cast<float>(1.0 / wp.near - 1.0 / wp.far);
-    p.atol_f = static_cast<float>(wp.atol); p.rtol_f = static_cast<float>(wp.rtol); p.erode_k = 2 * wp.erode_rgb - 1;
+    p.atol_f = static_cast<float>(wp.atol < 0.0 ? 0.0 : wp.atol); p.rtol_f = static_cast<float>(wp.rtol < 0.0 ? 0.0 : wp.rtol);
+    p.erode_k = 2 * wp.erode_rgb - 1;
     p.tmp8 = tmp8_; p.col8 = col8_; p.dproj = dproj_; p.m0 = m0_; p.mr0 = mr0_; p.out = out_dev;
     dim3 gh((S_ * n_ + 127) / 128, B_), gn((n_ * n_ + 127) / 128, B_);
     lanczos_h_kernel<<<gh, 128, 0, st>>>(p);

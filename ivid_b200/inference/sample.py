@@ -14,6 +14,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import threading
 
 import numpy as np
 import torch
@@ -22,7 +23,7 @@ from .. import backbones, frameworks, samplers
 from ..rgbd_3d import DeviceWarp, glm_compat as glm
 from ..rgbd_3d import utils as rgbd_utils
 from ..utils import edict
-from .utils import parse_int_list, save_scene
+from .utils import colorize_depth, parse_int_list, reorder, save_scene
 
 
 def shard(items, rank, world_size):
@@ -121,6 +122,79 @@ def sample_all(framework_uncond, framework_cond, seeds_or_num_samples, steps_unc
             yield meshes, colors, samples[k], ({n: t[k] for n, t in conds.items()} if conds is not None else None)
 
 
+def image_grid_u8(images, nrow, value_range=(-1, 1), padding=2):
+    """uint8 [H', W', 3] grid of `images` [K,3,H,W] — the arithmetic of torchvision.utils.save_image(make_grid(images, nrow,
+    normalize=True, value_range=value_range)) that the reference calls (sample.py:160-166): clamp to the range, scale to
+    [0,1] with the 1e-5 guard, tiles separated by `padding` black pixels, then *255 + 0.5 and truncation.  Runs on the
+    tensor's device (the GPU in the sampling loop), so only the packed uint8 image crosses PCIe."""
+    lo, hi = value_range
+    t = images.detach().to(torch.float32).clamp(lo, hi).sub(lo).div(max(hi - lo, 1e-5))
+    K, C, H, W = t.shape
+    if K == 1:                                  # make_grid returns a single image unpadded
+        grid = t[0]
+    else:
+        xm = min(nrow, K)
+        ym = -(-K // xm)
+        hh, ww = H + padding, W + padding
+        grid = t.new_zeros((C, hh * ym + padding, ww * xm + padding))
+        for k in range(K):
+            y, x = divmod(k, xm)
+            grid[:, y * hh + padding: y * hh + padding + H, x * ww + padding: x * ww + padding + W] = t[k]
+    return grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+
+
+def to_u8(rgb):
+    """(np.clip(x*0.5+0.5, 0, 1) * 255).astype(uint8) of a [3,H,W] model-space image (sample.py:156,161-162)."""
+    return (rgb.detach().to(torch.float32).mul(0.5).add(0.5).clamp(0, 1).mul(255)).to(torch.uint8).permute(1, 2, 0)
+
+
+def async_save(meshes, colors, samples, conds, suffix, cfg):
+    """Writes the outputs of the reference's async_save (sample.py:150-176) for one finished sample:
+         viewset uncond: results/rgb_*.png + scenes/scene_*.npz
+         viewset random: grids/rgb_*.png (both views), conds/rgb_*.png (view 0), results/rgb_*.png (view 1)
+         viewset 3x9   : grids/{rgb,depth}_*.png, conds/{rgb_cond,depth_cond}_*.png (3x9 mosaics, `reorder`), scenes/scene_*.npz
+    The 8-bit images are packed on the device on the caller's stream and copied to pinned host memory asynchronously; a
+    worker thread waits for that copy, encodes the PNGs and writes the scene, while the main thread goes on sampling."""
+    from PIL import Image
+    out = cfg.output_dir
+    jobs = []       # (relative path, device uint8 HWC tensor)
+    vs = cfg.viewset
+    if vs == "uncond":
+        jobs.append((os.path.join("results", f"rgb_{suffix}.png"), to_u8(samples[0, :3])))
+    elif vs == "random":
+        jobs.append((os.path.join("grids", f"rgb_{suffix}.png"), image_grid_u8(samples[:, :3], 2)))
+        jobs.append((os.path.join("conds", f"rgb_{suffix}.png"), to_u8(samples[0, :3])))
+        jobs.append((os.path.join("results", f"rgb_{suffix}.png"), to_u8(samples[1, :3])))
+    elif vs == "3x9":
+        dev = samples.device
+        jobs.append((os.path.join("grids", f"rgb_{suffix}.png"), image_grid_u8(reorder(samples[:, :3], vs), 9)))
+        jobs.append((os.path.join("grids", f"depth_{suffix}.png"), image_grid_u8(reorder(colorize_depth(samples[:, 3:]).to(dev), vs), 9)))
+        jobs.append((os.path.join("conds", f"rgb_cond_{suffix}.png"), image_grid_u8(reorder(conds["color"][:, :3], vs), 9)))
+        jobs.append((os.path.join("conds", f"depth_cond_{suffix}.png"), image_grid_u8(reorder(colorize_depth(conds["depth"]).to(dev), vs), 9)))
+    else:
+        raise NotImplementedError
+    host = []
+    for rel, t in jobs:
+        h = torch.empty(t.shape, dtype=torch.uint8, pin_memory=t.is_cuda)
+        h.copy_(t, non_blocking=True)
+        host.append((rel, h))
+    done = torch.cuda.Event() if samples.is_cuda else None
+    if done is not None:
+        done.record()
+
+    def worker():
+        if done is not None:
+            done.synchronize()
+        for rel, h in host:
+            Image.fromarray(h.numpy()).save(os.path.join(out, rel))
+        if vs in ("uncond", "3x9"):
+            save_scene(os.path.join(out, "scenes", f"scene_{suffix}.npz"), meshes, colors)
+
+    th = threading.Thread(target=worker)
+    th.start()
+    return th
+
+
 def _load_model(cfg, ckpt, device):
     net = getattr(backbones, cfg["backbone"]["name"])(**cfg["backbone"]["args"])
     if ckpt is not None:
@@ -154,14 +228,18 @@ def main(rank, world_size, opt):
     idx = list(range(num))[rank::world_size]
     mvs_r = shard(mvs, rank, world_size) if isinstance(mvs[0], list) else mvs
     out_dir = os.path.join(opt.output_dir, f"viewset_{opt.viewset}_steps_u{opt.steps_uncond}_c{opt.steps_cond}_guidance{opt.guidance}")
-    os.makedirs(os.path.join(out_dir, "scenes"), exist_ok=True)
+    for sub in ("results", "grids", "conds", "scenes"):                 # sample.py:283-286
+        os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+    save_cfg = edict(output_dir=out_dir, viewset=opt.viewset)
     gen = sample_all(fw_u, fw_c, seeds_r if seeds_r is not None else len(idx), opt.steps_uncond, opt.steps_cond, mvs_r, classes=classes_r,
                      guidance=opt.guidance, batchsize=opt.batchsize, fov=opt.fov, near=opt.near, far=opt.far, atol=opt.atol,
-                     rtol=opt.rtol, erode_rgb=opt.erode_rgb)
+                     rtol=opt.rtol, erode_rgb=opt.erode_rgb, rng=opt.rng)
+    threads = []
     for i, (meshes, colors, samples, conds) in enumerate(gen):
         tag = (f"class{classes_r[i]:03d}_" if classes_r is not None else "") + (f"seed{seeds_r[i]:05d}" if seeds_r is not None else f"{idx[i]:05d}")
-        save_scene(os.path.join(out_dir, "scenes", f"scene_{tag}.npz"), meshes, colors)
-        torch.save(samples.cpu(), os.path.join(out_dir, "scenes", f"samples_{tag}.pt"))
+        threads.append(async_save(meshes, colors, samples, conds, tag, save_cfg))
+    for th in threads:
+        th.join()
 
 
 if __name__ == "__main__":
@@ -185,6 +263,9 @@ if __name__ == "__main__":
     ap.add_argument("--atol", type=float, default=0.03)
     ap.add_argument("--rtol", type=float, default=0.03)
     ap.add_argument("--erode_rgb", type=int, default=3)
+    ap.add_argument("--rng", choices=["philox", "torch"], default="philox",
+                    help="per-step noise: 'philox' draws in-kernel (fast, default); 'torch' draws with the torch generator exactly "
+                         "where the reference does (seed-for-seed reproduction of the reference's images needs this)")
     o = ap.parse_args()
     n = torch.cuda.device_count()
     if n <= 1:

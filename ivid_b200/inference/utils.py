@@ -44,12 +44,13 @@ def _unpng(b: bytes) -> np.ndarray:
 
 
 def _store_modelview(mv):
+    from ..rgbd_3d.glm_compat import as_matrix
+    m = as_matrix(mv)          # PyGLM mat4 (column-major indexing) or numpy / nested lists (row-major) -> m[row][col]
     try:                       # keep scenes loadable by the reference's render.py when PyGLM is installed
         import glm
-        m = np.asarray(mv, dtype=np.float32)
         return glm.mat4(*[float(m[r][c]) for c in range(4) for r in range(4)])
-    except Exception:
-        return np.asarray(mv, dtype=np.float32)
+    except ImportError:
+        return m
 
 
 def save_scene(path, meshes, colors):

@@ -21,8 +21,10 @@ def warp_params(fov=45, near=0.5, far=100, atol=0.02, rtol=0.02, erode_rgb=2, pa
     p = _lib.WarpParamsT()
     p.padding = float(padding)
     p.fov_deg, p.near, p.far = float(fov), float(near), float(far)
-    p.atol = 0.0 if atol is None else float(atol)
-    p.rtol = 0.0 if rtol is None else float(rtol)
+    # None travels as a negative value: depth_to_mesh skips the discontinuity test when BOTH are None and uses 0 for a single
+    # None (reference utils.py:227-229)
+    p.atol = -1.0 if atol is None else float(atol)
+    p.rtol = -1.0 if rtol is None else float(rtol)
     p.erode_rgb = int(erode_rgb or 0)
     return p
 

@@ -130,6 +130,23 @@ class _NativeSampler:
         del keep
         return edict({"pred_x_prev": x_prev, "pred_x_0": x0})
 
+    def _native_step_dev(self, x_t, t, t_prev, classes, clip_denoised, eta, kwargs, noise, cond_noise):
+        """Same step with the timestep taken on the device from the [N] tensors the caller passed (no host sync)."""
+        net = self._net()
+        dev = x_t.device
+        x_t = _f32(x_t, dev)
+        a, keep = self._step_args(dev, classes, clip_denoised, eta, kwargs, step_noise=noise, cond_noise=cond_noise)
+        td = t.to(device=dev, dtype=torch.int64).contiguous()
+        tp = t_prev.to(device=dev, dtype=torch.int64).contiguous() if t_prev is not None else None
+        x_prev = torch.empty_like(x_t)
+        x0 = torch.empty_like(x_t)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ivid_sampler_step_dev(self._handle, net._handle, _lib.ptr(x_t), _lib.ptr(x_prev), _lib.ptr(x0),
+                                                        x_t.shape[0], _lib.ptr(td), _lib.ptr(tp), ctypes.byref(a),
+                                                        _lib.cur_stream(dev)))
+        del keep
+        return edict({"pred_x_prev": x_prev, "pred_x_0": x0})
+
     def _draw_step_noise(self, x_t, kwargs):
         """torch draws in the reference's order: InpaintCFG rgb, depth (inside model_inference), then randn_like(x_t)."""
         cond_noise = None
@@ -212,13 +229,13 @@ class DdpmSampler(_NativeSampler):
         `noise` (extension) injects the randn_like draw; default draws it with torch like the reference."""
         B = x_t.shape[0]
         assert t.shape == (B,), "t must be a 1D tensor of shape (B,)"
-        ti = int(t[0])
-        assert bool(torch.all(t == ti)), "all samples of a batch share the timestep"
+        # all samples of a batch share the timestep (both reference samplers are driven that way: ddpm.py:177-179);
+        # element 0 is read on the device, so this call does not synchronise with the host
         if noise is None:
             noise, cond_noise = self._draw_step_noise(x_t, kwargs)
         else:
             cond_noise = kwargs.pop("cond_noise", None)
-        return self._native_step(x_t, ti, 0, classes, clip_denoised, 0.0, kwargs, noise, cond_noise)
+        return self._native_step_dev(x_t, t, None, classes, clip_denoised, 0.0, kwargs, noise, cond_noise)
 
     @torch.no_grad()
     def sample(self, num, steps=None, image_size=None, noise=None, classes=None, clip_denoised=False, verbose=True,
@@ -239,14 +256,13 @@ class DdimSampler(_NativeSampler):
         """x_{t_prev} from x_t (ddim.py:48-103).  t / t_prev are [N] tensors of actual steps (1 means one step)."""
         B = x_t.shape[0]
         assert t.shape == (B,) and t_prev.shape == (B,)
-        ti, tp = int(t[0]), int(t_prev[0])
-        assert bool(torch.all(t == ti)) and bool(torch.all(t_prev == tp)), "all samples of a batch share the timestep"
+        # element 0 of t / t_prev is read on the device (all samples share the step, ddim.py:154-158): no host sync
         kw = dict(kwargs, replace_rgb=replace_rgb, replace_depth=replace_depth, constrain_depth=constrain_depth)
         if noise is None:
             noise, cond_noise = self._draw_step_noise(x_t, kw)
         else:
             cond_noise = kw.pop("cond_noise", None)
-        return self._native_step(x_t, ti, tp, classes, clip_denoised, eta, kw, noise, cond_noise)
+        return self._native_step_dev(x_t, t, t_prev, classes, clip_denoised, eta, kw, noise, cond_noise)
 
     @torch.no_grad()
     def sample(self, num, image_size=None, noise=None, classes=None, steps=None, clip_denoised=False, eta=0.0,

@@ -1,7 +1,9 @@
 """GPU parity of the fused denoising steps (teacher-forced: the oracle's x_t is fed at every step) and of the
 size-independent properties of the whole sampler.
 
-Tolerance (north star): x_{t-1} within 1e-3 relative of the fp32 reference per denoising step."""
+Tolerance (north star): x_{t-1} within 1e-3 relative of the fp32 reference per denoising step (STEP_TOL).  On top of that
+every case asserts a regression bound = the value measured on B200 (round 1 / round 2 builds) + ~30 %, so that a
+precision regression far inside the north-star bar is still caught."""
 import json
 
 import numpy as np
@@ -38,7 +40,7 @@ def test_ddpm_steps_vs_reference_golden(golden):
         out = s.sample_once(x_t, t, classes, strength=0.5, noise=torch.from_numpy(golden[f"ddpm_t{ti}_noise"]).cuda())
         r = G.report(f"ddpm step t={ti} x_prev", out.pred_x_prev, torch.from_numpy(golden[f"ddpm_t{ti}_xprev"]))
         r0 = G.report(f"ddpm step t={ti} x_0", out.pred_x_0, torch.from_numpy(golden[f"ddpm_t{ti}_x0"]))
-        assert r < STEP_TOL
+        assert r < STEP_TOL and r < 4e-5            # measured <= 2.2e-5: DDPM damps the eps error by ~0.02
         assert r0 < (0.5 if ti > 900 else 5e-3)     # x_0 = 157*(x_t - eps) at t=999: ill-conditioned by construction
 
 
@@ -57,7 +59,7 @@ def test_ddim_guided_steps_vs_reference_golden(golden):
                             replace_depth=(0.2, y[:, 3:], mask), constrain_depth=(0.5, convex),
                             noise=torch.zeros_like(x_t), cond_noise=cn)
         r = G.report(f"ddim guided step {tt}->{tp} x_prev", out.pred_x_prev, torch.from_numpy(golden[f"ddim_t{tt}_xprev"]))
-        assert r < STEP_TOL
+        assert r < STEP_TOL and r < 2.6e-4          # measured 0.8e-4 .. 1.9e-4
 
 
 def test_framework_model_inference_cfg(golden):
@@ -70,9 +72,11 @@ def test_framework_model_inference_cfg(golden):
     model = lambda x, tt, c: unet_ref.unet_forward(cfg, sd, x, tt, c)
     ref = sampler_ref.cfg_eps(model, x_t, t, classes, 3.0)
     got = fw.model_inference(x_t.cuda(), t.cuda(), classes.cuda(), strength=3.0)
-    assert G.report("cfg model_inference s=3", got, ref) < 4e-3
+    # (1+s)*e_c - s*e_u with s = 3 amplifies the relative eps error (independent errors: x5; measured x2, the two halves share
+    # x and the weight roundings): measured 1.9e-3
+    assert G.report("cfg model_inference s=3", got, ref) < 2.5e-3
     got0 = fw.model_inference(x_t.cuda(), t.cuda(), classes.cuda(), strength=0.0)
-    assert G.report("cfg model_inference s=0", got0, model(x_t, t, classes)) < 3e-3
+    assert G.report("cfg model_inference s=0", got0, model(x_t, t, classes)) < 1.15e-3       # plain eps: tests/test_gpu_unet.py bars
 
 
 def test_full_ddim_run_teacher_forced_and_free(golden):
@@ -96,9 +100,8 @@ def test_full_ddim_run_teacher_forced_and_free(golden):
         out = s.sample_once(xo.cuda(), t.cuda(), tpv.cuda(), classes.cuda(), strength=0.5, noise=torch.zeros_like(xo).cuda())
         worst = max(worst, G.report(f"ddim-10 teacher-forced {tt}->{tp}", out.pred_x_prev, ref))
         xo = ref
-    # DDIM-10 amplifies eps error by up to 1.6x per step: 1e-3 on x_{t-1} needs eps <= 6e-4,
-    # beyond fp16/TF32-class operands; the bar is met for DDPM and DDIM-50 and reported here for DDIM-10.
-    assert worst < 5e-3
+    # DDIM-10 amplifies the eps error by up to 1.6x per step; measured worst step 6.0e-4
+    assert worst < STEP_TOL and worst < 7.8e-4
     # whole-loop == chained single steps (bitwise)
     xa = x.clone().cuda()
     for (tt, tp) in sampler_ref.ddim_schedule(1000, 10):
@@ -138,8 +141,8 @@ def test_superres_ddim_step_vs_oracle(golden):
         eps = sampler_ref.cond_eps(model, sampler_ref.make_sr_inputs(x, y), t - 1, classes, 3.0)
         ref, _ = sampler_ref.ddim_step(tb, x, t, tpv, eps, torch.zeros_like(x))
         out = s.sample_once(x.cuda(), t.cuda(), tpv.cuda(), classes.cuda(), strength=3.0, y=y.cuda(), noise=torch.zeros_like(x).cuda())
-        assert G.report(f"superres ddim step {tt}->{tp}", out.pred_x_prev, ref) < 2e-3     # guidance 3.0 amplifies eps error 4x
-    # the framework-level call (python make_cond_inputs + batched CFG forward) agrees with the fused native path
+        assert G.report(f"superres ddim step {tt}->{tp}", out.pred_x_prev, ref) < 8e-4     # measured 3e-4 .. 6.1e-4 at guidance 3.0
+    # the framework-level call (same fused native assembly + batch-2N forward + native CFG mix)
     got = fw.model_inference(x.cuda(), torch.tensor([499, 499]).cuda(), y.cuda(), classes.cuda(), strength=3.0)
     ref_eps = sampler_ref.cond_eps(model, sampler_ref.make_sr_inputs(x, y), torch.tensor([499, 499]), classes, 3.0)
-    assert G.report("superres model_inference", got, ref_eps) < 6e-3
+    assert G.report("superres model_inference", got, ref_eps) < 3.5e-3                    # guidance 3.0: see test_framework_model_inference_cfg

@@ -1,10 +1,21 @@
 """GPU parity of the whole AdmUnet2d forward (through the reference-facing class and the C ABI) against
- (a) the committed golden vectors produced by the unmodified reference (tiny configs), and
- (b) the CPU oracle on the real configs (small / large), computed in-test at N=1..2.
+ (a) the committed golden vectors produced by the unmodified reference (tiny configs),
+ (b) the CPU oracle on the real configs (small / large / cond / SR), computed in-test,
+ (c) the oracle's per-layer taps (ivid_unet_debug_tap).
 
-Tolerance: eps within 3e-3 relative L2 of the fp32 reference (fp16 tensor-core operands, fp32 everything else; the
-reference's own fp16 torso is 1.7e-3 from its fp32 path).  Per denoising step this is <= 1e-3 in
-x_{t-1} for DDPM and DDIM-50 (tests/test_gpu_sampler.py)."""
+Tolerance on eps (relative L2 against the strict-fp32 oracle).  The tensor-core operands are fp16 (10-bit mantissa, the
+mantissa of TF32); everything between the GEMMs is fp32 or a single extra fp16 rounding (tests/precision_model.py lists
+every one).  The bar per case is
+
+        max(1e-3, 1.15 x floor)        and never above 1.6e-3,
+
+where `floor` is computed IN THE SAME TEST: the oracle with only its conv / GEMM operands rounded to a 10-bit mantissa —
+what the unmodified reference itself computes on the A100 it was tested on (PyTorch 1.11 runs fp32 convolutions and
+matmuls in TF32 by default).  For most cases the floor is below 0.87e-3 and the bar is the north star's 1e-3; where the
+reference's own GPU arithmetic is already further than 1e-3 from strict fp32 (tiny_cond: 1.2e-3) no 10-bit-operand
+implementation can do better, and the test says so instead of hiding it behind a loose constant.
+Per denoising step (x_{t-1}) the 1e-3 bar is met with a wide margin: tests/test_gpu_sampler.py."""
+import ctypes
 import json
 
 import numpy as np
@@ -13,10 +24,17 @@ import torch
 
 import gpu_util as G
 import ivid_b200.backbones as backbones
+import precision_model as PM
+from ivid_b200 import _lib
 from oracle import unet_ref
 
 pytestmark = pytest.mark.gpu
-EPS_TOL = 3e-3
+NORTH_STAR = 1e-3
+HARD_CAP = 1.6e-3
+
+
+def _bar(floor):
+    return min(max(NORTH_STAR, 1.15 * floor), HARD_CAP)
 
 
 def _load(cfg, sd):
@@ -25,31 +43,44 @@ def _load(cfg, sd):
     return net.cuda()
 
 
+def _check(name, got, ref, cfg, sd, x, t, c):
+    floor = PM.rel(PM.forward(cfg, sd, x, t, c, PM.TF32_CLASS), ref)
+    err = G.report(name, got, ref)
+    print(f"[parity] {name}: eps rel {err:.3e}  TF32-class floor {floor:.3e}  bar {_bar(floor):.3e}")
+    assert err <= _bar(floor), f"{name}: eps rel {err:.3e} > bar {_bar(floor):.3e} (floor {floor:.3e})"
+    return err, floor
+
+
 @pytest.mark.parametrize("tag", ["tiny", "tiny_cond", "tiny_sr"])
 def test_tiny_unet_vs_reference_golden(golden, tag):
     cfg = json.loads(bytes(golden[f"{tag}_cfg"]).decode())
     sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
     net = _load(cfg, sd)
-    x = torch.from_numpy(golden[f"{tag}_x"]).cuda(); t = torch.from_numpy(golden[f"{tag}_t"]).cuda()
-    c = torch.from_numpy(golden[f"{tag}_classes"]).cuda()
-    r1 = G.report(f"{tag} unet eps (classes)", net(x, t, c), torch.from_numpy(golden[f"{tag}_eps"]))
-    r2 = G.report(f"{tag} unet eps (None)", net(x, t, None), torch.from_numpy(golden[f"{tag}_eps_none"]))
-    assert r1 < EPS_TOL and r2 < EPS_TOL
-    # determinism: same inputs, same bits
-    assert torch.equal(net(x, t, c), net(x, t, c))
+    x = torch.from_numpy(golden[f"{tag}_x"]); t = torch.from_numpy(golden[f"{tag}_t"]); c = torch.from_numpy(golden[f"{tag}_classes"])
+    _check(f"{tag} unet eps (classes)", net(x.cuda(), t.cuda(), c.cuda()), torch.from_numpy(golden[f"{tag}_eps"]), cfg, sd, x, t, c)
+    _check(f"{tag} unet eps (None)", net(x.cuda(), t.cuda(), None), torch.from_numpy(golden[f"{tag}_eps_none"]), cfg, sd, x, t, None)
+    # determinism: same inputs, same bits (eager first call, CUDA-graph replays afterwards)
+    a = net(x.cuda(), t.cuda(), c.cuda())
+    assert torch.equal(a, net(x.cuda(), t.cuda(), c.cuda())) and torch.equal(a, net(x.cuda(), t.cuda(), c.cuda()))
 
 
-def test_layerwise_taps_tiny(golden):
-    """Per-layer drift: run the oracle with taps and compare the CUDA output head only — plus report where a
-    divergence would start by re-running the oracle on the tiny config with one sample."""
+def test_eps_seeds_and_timesteps_fp32_tiny(golden):
+    """use_fp16=False config, 3 weight/input seeds x t in {999, 500, 37}: every case within its bar."""
     cfg = json.loads(bytes(golden["tiny_cfg"]).decode())
-    sd = unet_ref.make_synthetic_state_dict(cfg, seed=99)
-    net = _load(cfg, sd)
-    rng = np.random.default_rng(3)
-    x = torch.from_numpy(rng.standard_normal((1, 4, 32, 32)).astype(np.float32))
-    t = torch.tensor([250]); c = torch.tensor([4])
-    ref = unet_ref.unet_forward(cfg, sd, x, t, c)
-    assert G.report("tiny seed99 N=1", net(x.cuda(), t.cuda(), c.cuda()), ref) < EPS_TOL
+    assert not cfg["use_fp16"]
+    worst = 0.0
+    for seed in (1234, 99, 7):
+        sd = unet_ref.make_synthetic_state_dict(cfg, seed=seed)
+        net = _load(cfg, sd)
+        rng = np.random.default_rng(seed)
+        x = torch.from_numpy(rng.standard_normal((2, 4, 32, 32)).astype(np.float32))
+        c = torch.tensor([4, -1])
+        for tt in (999, 500, 37):
+            t = torch.tensor([tt, tt])
+            ref = unet_ref.unet_forward(cfg, sd, x, t, c)
+            err, _ = _check(f"tiny seed{seed} t={tt}", net(x.cuda(), t.cuda(), c.cuda()), ref, cfg, sd, x, t, c)
+            worst = max(worst, err)
+    print(f"[parity] tiny fp32, 3 seeds x 3 timesteps: worst eps rel {worst:.3e}")
 
 
 @pytest.mark.parametrize("name,N", [("rgbd_singlecategory_adm_128_small", 1), ("rgbd_imagenet_adm_128_large_cfg", 2),
@@ -63,7 +94,57 @@ def test_real_config_vs_oracle(golden, name, N):
     x = torch.from_numpy(rng.standard_normal((N, cfg["in_channels"], S, S)).astype(np.float32))
     t = torch.tensor([999, 37][:N])
     c = torch.tensor([3, -1][:N]) if cfg.get("num_classes") else None
-    torch.set_num_threads(max(1, torch.get_num_threads()))
     ref = unet_ref.unet_forward(cfg, sd, x, t, c)
     got = net(x.cuda(), t.cuda(), c.cuda() if c is not None else None)
-    assert G.report(f"{name} N={N} eps", got, ref) < EPS_TOL
+    _check(f"{name} N={N} eps", got, ref, cfg, sd, x, t, c)
+
+
+def test_large_fp32_config_three_timesteps(golden):
+    """The headline model (rgbd_imagenet_adm_128_large_cfg, use_fp16=False) at t in {999, 500, 37}, fresh input seed each."""
+    cfg = json.loads(bytes(golden["schemacfg_rgbd_imagenet_adm_128_large_cfg"]).decode())
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
+    net = _load(cfg, sd)
+    for seed, tt in ((21, 999), (22, 500), (23, 37)):
+        rng = np.random.default_rng(seed)
+        x = torch.from_numpy(rng.standard_normal((1, 4, 128, 128)).astype(np.float32))
+        t = torch.tensor([tt]); c = torch.tensor([seed])
+        ref = unet_ref.unet_forward(cfg, sd, x, t, c)
+        _check(f"large seed{seed} t={tt}", net(x.cuda(), t.cuda(), c.cuda()), ref, cfg, sd, x, t, c)
+
+
+def _tap(net, N, name):
+    L = _lib.lib()
+    C, H, W = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(L.ivid_unet_debug_tap(net._handle, N, name.encode(), None, 0, ctypes.byref(C), ctypes.byref(H), ctypes.byref(W)))
+    out = torch.empty((N, C.value, H.value, W.value), dtype=torch.float32)
+    _lib.check(L.ivid_unet_debug_tap(net._handle, N, name.encode(), _lib.ptr(out), out.numel(), None, None, None))
+    return out
+
+
+@pytest.mark.parametrize("which", ["tiny", "large"])
+def test_layerwise_taps(golden, which):
+    """Per-layer drift: the output of EVERY ResBlock / AttentionBlock / the stem against the oracle's taps.  Shows where the
+    eps error is accumulated (it grows smoothly along the depth: no single layer is off) and pins each block on its own."""
+    key = "tiny_cfg" if which == "tiny" else "schemacfg_rgbd_imagenet_adm_128_large_cfg"
+    cfg = json.loads(bytes(golden[key]).decode())
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=99 if which == "tiny" else 1234)
+    net = _load(cfg, sd)
+    S = cfg["image_size"]
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((1, 4, S, S)).astype(np.float32))
+    t = torch.tensor([250]); c = torch.tensor([4])
+    taps = {}
+    ref = unet_ref.unet_forward(cfg, sd, x, t, c, taps=taps)
+    got = net(x.cuda(), t.cuda(), c.cuda())
+    worst, worst_name = 0.0, ""
+    for name, want in taps.items():
+        if name == "emb":
+            continue
+        r = G.rel(_tap(net, 1, name), want)
+        print(f"[tap] {which:5s} {name:24s} {tuple(want.shape)!s:22s} rel {r:.3e}")
+        if r > worst:
+            worst, worst_name = r, name
+    # the stem carries a two-term split of x and W: it must be far inside fp16 precision
+    assert G.rel(_tap(net, 1, "input_blocks.0.0"), taps["input_blocks.0.0"]) < 2e-5
+    assert worst < 1.2e-3, f"layer {worst_name} is {worst:.3e} from the oracle"
+    _check(f"{which} taps run eps", got, ref, cfg, sd, x, t, c)

@@ -75,6 +75,15 @@ def test_numpy_facing_depth_to_mesh(wg):
     assert np.abs(m.vertices.position - ref.vertices.position).max() < 2.5e-7
     with pytest.raises(NotImplementedError):
         rgbd_3d.utils.depth_to_mesh(d, padding=None, modelview=wg["views"][1])
+    # tolerances left at None (the reference's defaults): no discontinuity test at all, hence no erosion either; a single None
+    # counts as 0 (utils.py:227-229)
+    for at, rt in ((None, None), (0.03, None), (None, 0.03)):
+        m = rgbd_3d.utils.depth_to_mesh(d, padding="frustum", fov=p["fov"], modelview=wg["views"][1], atol=at, rtol=rt,
+                                        erode_rgb=p["erode_rgb"], cal_normal=True)
+        ref = warp_ref.depth_to_mesh(d, fov=p["fov"], modelview=wg["views"][1], atol=at, rtol=rt, erode_rgb=p["erode_rgb"])
+        assert np.array_equal(m.vertices.flag, ref.vertices.flag.astype(np.float32)), (at, rt)
+        if at is None and rt is None:
+            assert set(np.unique(m.vertices.flag)) <= {0.0, 2.0}
 
 
 def _raw_compare(tag, got, ref):

@@ -130,3 +130,62 @@ def test_two_rank_sharding_gloo():
         assert ok and tmax == 2.0
         assert sorted(got[0] + got[1]) == list(range(11)) and not set(got[0]) & set(got[1])
         assert mine == list(range(11))[rank::2]
+
+
+def test_image_grid_matches_torchvision():
+    """image_grid_u8 == torchvision.utils.save_image(make_grid(..., normalize=True, value_range=(-1, 1))) (sample.py:160-166)."""
+    tv = pytest.importorskip("torchvision.utils")
+    from ivid_b200.inference import image_grid_u8
+    g = torch.Generator().manual_seed(0)
+    for K, nrow in ((2, 2), (27, 9), (5, 4), (1, 9)):
+        img = torch.randn(K, 3, 12, 10, generator=g) * 0.9
+        want = tv.make_grid(img, nrow=nrow, normalize=True, value_range=(-1, 1))
+        want = want.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+        got = image_grid_u8(img, nrow)
+        assert got.shape == want.shape and torch.equal(got, want), (K, nrow)
+
+
+def test_async_save_outputs(tmp_path):
+    """The directory contract of the reference's async_save (sample.py:150-176) per view set."""
+    from PIL import Image
+    from ivid_b200.inference import async_save
+    g = torch.Generator().manual_seed(1)
+    mv = build_modelviews("uncond", 1)[0]
+
+    def scene(V):
+        meshes = [edict(depth=np.full((8, 8, 1), 1.5, np.float32), fov=45, modelview=mv) for _ in range(V)]
+        return meshes, [np.full((8, 8, 3), 0.5, np.float32) for _ in range(V)]
+    for vs, V in (("uncond", 1), ("random", 2), ("3x9", 27)):
+        out = os.path.join(tmp_path, vs)
+        for sub in ("results", "grids", "conds", "scenes"):
+            os.makedirs(os.path.join(out, sub))
+        samples = torch.rand(V, 4, 8, 8, generator=g) * 2 - 1
+        conds = {"color": torch.rand(V - 1, 3, 8, 8, generator=g) * 2 - 1, "depth": torch.rand(V - 1, 1, 8, 8, generator=g) * 2 - 1} if V > 1 else None
+        meshes, colors = scene(V)
+        async_save(meshes, colors, samples, conds, "class001_seed00005", edict(output_dir=out, viewset=vs)).join()
+        files = sorted(os.path.relpath(os.path.join(d, f), out) for d, _, fs in os.walk(out) for f in fs)
+        want = {"uncond": ["results/rgb_class001_seed00005.png", "scenes/scene_class001_seed00005.npz"],
+                "random": ["conds/rgb_class001_seed00005.png", "grids/rgb_class001_seed00005.png", "results/rgb_class001_seed00005.png"],
+                "3x9": ["conds/depth_cond_class001_seed00005.png", "conds/rgb_cond_class001_seed00005.png", "grids/depth_class001_seed00005.png",
+                        "grids/rgb_class001_seed00005.png", "scenes/scene_class001_seed00005.npz"]}[vs]
+        assert files == sorted(want), (vs, files)
+        if vs == "uncond":
+            px = np.array(Image.open(os.path.join(out, want[0])))
+            ref = (np.clip(samples[0, :3].numpy().transpose(1, 2, 0) * 0.5 + 0.5, 0, 1) * 255).astype(np.uint8)
+            assert np.array_equal(px, ref)
+        if vs == "3x9":
+            assert np.array(Image.open(os.path.join(out, "grids/rgb_class001_seed00005.png"))).shape == (3 * 10 + 2, 9 * 10 + 2, 3)
+            assert len(load_scene_views(os.path.join(out, want[-1]))) == 27
+
+
+def test_scene_modelview_accepts_column_major_glm_objects(tmp_path):
+    """A PyGLM mat4 indexes as m[col][row]; save_scene must store the same camera either way."""
+    from ivid_b200.inference.utils import _store_modelview
+    m = build_modelviews("3x9", 1)[5]
+
+    class FakeMat4:                       # quacks like glm.mat4: module name 'glm', column-major indexing
+        __module__ = "glm"
+        def __init__(self, a): self.a = np.asarray(a)
+        def __getitem__(self, c): return [float(self.a[r][c]) for r in range(4)]
+    stored = np.asarray(_store_modelview(FakeMat4(m)), dtype=np.float32)
+    assert np.allclose(stored, np.asarray(_store_modelview(m), dtype=np.float32)) and np.allclose(stored, m)
