@@ -166,7 +166,8 @@ typedef struct {
   double rtol;      /* sample.py:262;   exactly one None -> that tolerance is 0.  Other entry points take a negative value as 0.      */
   int erode_rgb;    /* sample.py:263 */
   double padding;   /* depth_to_mesh padding: 0 = 'frustum' (sample.py:131: ring pushed out one pixel and pulled to z = -0.1);
-                       > 0 = that many pixels, ring not pulled (inference/utils.py:107 load_scene uses 32 for free-view rendering) */
+                       > 0 = that many pixels, ring not pulled (inference/utils.py:107 load_scene uses 32 for free-view rendering,
+                       datasets/base.py:238 uses image_size for the training-pair warp); < 0 = None: no ring, n*n vertices */
 } ivid_warp_params_t;
 
 /* [AggregationRenderer(render_size, image_size, near, far) for _ in range(batch)]  (sample.py:50) */
@@ -202,6 +203,22 @@ int ivid_warp_aggregate(ivid_warp_t* w, const float* target_mv_host, int shared_
  * 7-of-9 votes, depth_edge, erosion) on caller-provided raw renders. */
 int ivid_warp_postfilter(ivid_warp_t* w, const float* color_dev, const float* depth_dev, const float* mask_color_dev,
                          const float* mask_depth_dev, const ivid_warp_params_t* params, float* cond_dev, void* stream);
+
+/* Training-pair warp — replaces rgbd_3d.SimpleRenderer (moderngl_renderer.py:11-148, shaders/simple.{vsh,fsh}) and
+ * rgbd_3d.utils.forward_backward_warp (utils.py:335-417; called per training item by datasets/base.py:215-266).
+ * SimpleRenderer.render(mesh, color, modelview, fov) for a single-sample handle: the mesh is an image_size^2 (padding=None)
+ * or (image_size+2)^2 grid mesh in the 9-float vertex layout of ivid_warp_set_mesh (normals unused); outputs at render size
+ * S on the host: color [S,S,3], depth [S,S] (linearised with the handle's near / far), mask [S,S] (alpha > 0.5 as 0/1). */
+int ivid_warp_render_simple(ivid_warp_t* w, const float* verts_host, int nverts, const uint32_t* faces_host, int nfaces,
+                            const float* color_host, const float* target_mv_host, double fov_deg, float* color_out_host,
+                            float* depth_out_host, float* mask_out_host, void* stream);
+/* forward_backward_warp for every sample of the handle's batch, device resident between the two renders:
+ *   lin_depth0_host [batch,H,W] = linearize_depth(rgbd[..., 3:], near, far), color0_host [batch,H,W,3] = rgbd[..., :3];
+ *   mv1 / mv0 [batch][16] (or one shared matrix each); params: padding (of the first mesh), fov, near, far, atol, rtol;
+ *   out_host [batch,7,H,W]: color(3), depth, mask, mask, projected depth before masking. */
+int ivid_warp_forward_backward(ivid_warp_t* w, const float* lin_depth0_host, const float* color0_host, const float* mv1_host,
+                               const float* mv0_host, int shared_modelview, const ivid_warp_params_t* params, float* out_host,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Operator-level entry points (unit parity tests, profiling): the kernels the UNet is assembled from.

@@ -184,8 +184,11 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   const int64_t* cls = nullptr;
   if (has_classes) {
     if (cfg_two) {
-      fill_classes_kernel<<<1, 256, 0, stream>>>(a.classes_dev, d_classes2_, N);
-      IVID_CHECK_CUDA(cudaGetLastError());
+      // [classes, -1 ...] of the batch-2N forward; inside run() it is filled once for the whole reverse process
+      if (!(classes2_ready_ && classes2_src_ == a.classes_dev && classes2_n_ == N)) {
+        fill_classes_kernel<<<1, 256, 0, stream>>>(a.classes_dev, d_classes2_, N);
+        IVID_CHECK_CUDA(cudaGetLastError());
+      }
       cls = d_classes2_;
     } else {
       cls = a.classes_dev;
@@ -242,6 +245,14 @@ void Sampler::run(Unet& unet, float* x, int N, int steps, const ivid_step_args_t
   ensure_device(2 * N, 2 * img);
   float* bufs[2] = {x, d_xtmp_};                   // ping-pong; the result is copied back to x if it ends in d_xtmp_
   int cur = 0;
+  // per denoising step the host then issues three calls: the step-state kernel, ONE CUDA-graph launch (the whole batch-2N
+  // forward) and the fused guidance-mix + x_{t-1} update
+  struct Ready { Sampler* s; ~Ready() { s->classes2_ready_ = false; } } ready_guard{this};
+  if (a.use_cfg && a.classes_dev != nullptr && a.strength > 0.0f) {
+    fill_classes_kernel<<<1, 256, 0, stream>>>(a.classes_dev, d_classes2_, N);
+    IVID_CHECK_CUDA(cudaGetLastError());
+    classes2_ready_ = true; classes2_src_ = a.classes_dev; classes2_n_ = N;
+  }
   for (int i = 0; i < steps; ++i) {
     int t, t_prev;
     if (ddim) { t = jump * (steps - i); t_prev = jump * (steps - 1 - i); }   // ddim.py:154

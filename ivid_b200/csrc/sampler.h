@@ -32,6 +32,9 @@ class Sampler {
   int64_t* d_classes2_ = nullptr;
   float* d_eps_ = nullptr;
   float* d_xtmp_ = nullptr;
+  bool classes2_ready_ = false;            // d_classes2_ already holds [classes, -1 ...] for (classes2_src_, classes2_n_)
+  const int64_t* classes2_src_ = nullptr;
+  int classes2_n_ = 0;
   int cap_n_ = 0;
   size_t cap_eps_ = 0;
 };

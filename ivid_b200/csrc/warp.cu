@@ -130,6 +130,7 @@ struct RasterParams {
   const float* mvp;           // [B][16] row-major P*MV of the target view
   unsigned long long* vis;    // [B][nviews][S*S]
   int nviews, F, S;
+  int simple;                 // 1: SimpleRenderer (simple.fsh): no back-face padding discard
 };
 
 // One set-up sub-triangle, flattened to 32-bit words so a lane can broadcast it to its warp with shuffles.
@@ -164,7 +165,7 @@ __device__ __forceinline__ void rtri_make(const WVtx* v, int S, uint32_t prim, R
   r.valid = 1;
 }
 
-__device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis) {
+__device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis, int simple) {
   TriSetup t;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { t.X[i] = r.X[i]; t.Y[i] = r.Y[i]; t.zw[i] = r.zw[i]; t.iw[i] = r.iw[i]; }
@@ -173,7 +174,7 @@ __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S,
   if (!tri_eval(t, px, py, l0, l1, l2)) return;
   const float z = (l0 * t.zw[0] + l1 * t.zw[1]) + l2 * t.zw[2];
   if (!(z > 0.f && z < 1.f)) return;
-  if (!(r.area > 0)) {
+  if (!simple && !(r.area > 0)) {
     const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
     const float bs = (b0 + b1) + b2;
     const float pad = ((b0 / bs) * r.pad[0] + (b1 / bs) * r.pad[1]) + (b2 / bs) * r.pad[2];
@@ -185,13 +186,13 @@ __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S,
 
 // Small triangles (the common 3x3-pixel case) are scanned by their own lane; triangles with a large bounding box (the
 // frustum ring and faces stretched across depth discontinuities) are broadcast to the warp and scanned by all 32 lanes.
-__device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane) {
+__device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane, int simple) {
   constexpr int kSmall = 48;
   const int w = r.valid ? (r.px1 - r.px0 + 1) : 0, h = r.valid ? (r.py1 - r.py0 + 1) : 0;
   const bool big = r.valid && (w * h > kSmall);
   if (r.valid && !big) {
     for (int py = r.py0; py <= r.py1; ++py)
-      for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis);
+      for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis, simple);
   }
   unsigned mask = __ballot_sync(0xffffffffu, big);
   while (mask) {
@@ -213,9 +214,16 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
       eb[i] = (b.X[c] - b.X[a]) * sgn;
       ec[i] = -(ea[i] * b.X[a] + eb[i] * b.Y[a]);
     }
+    // The tiles of the bounding box are TESTED 32 at a time (one tile per lane; the frustum-ring slivers have bounding boxes
+    // of thousands of tiles of which a few dozen survive), the survivors are then scanned by the whole warp, 2 pixels per lane.
     const int tx0 = b.px0 >> 3, tx1 = b.px1 >> 3, ty0 = b.py0 >> 3, ty1 = b.py1 >> 3;
-    for (int ty = ty0; ty <= ty1; ++ty) {
-      for (int tx = tx0; tx <= tx1; ++tx) {
+    const int ntx = tx1 - tx0 + 1, nt = ntx * (ty1 - ty0 + 1);
+    for (int base = 0; base < nt; base += 32) {
+      const int ti = base + lane;
+      int tx = 0, ty = 0;
+      bool keep = false;
+      if (ti < nt) {
+        ty = ty0 + ti / ntx; tx = tx0 + ti % ntx;
         const int x0 = max(tx * 8, b.px0), x1 = min(tx * 8 + 7, b.px1), y0 = max(ty * 8, b.py0), y1 = min(ty * 8 + 7, b.py1);
         const long long cx0 = static_cast<long long>(x0) * 256 + 128, cx1 = static_cast<long long>(x1) * 256 + 128;
         const long long cy0 = static_cast<long long>(y0) * 256 + 128, cy1 = static_cast<long long>(y1) * 256 + 128;
@@ -225,10 +233,18 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
           const long long emax = ea[i] * (ea[i] > 0 ? cx1 : cx0) + eb[i] * (eb[i] > 0 ? cy1 : cy0) + ec[i];
           out = out || (emax < 0);
         }
-        if (out) continue;
+        keep = !out;
+      }
+      unsigned km = __ballot_sync(0xffffffffu, keep);
+      while (km) {
+        const int sl = __ffs(km) - 1;
+        km &= km - 1;
+        const int stx = __shfl_sync(0xffffffffu, tx, sl), sty = __shfl_sync(0xffffffffu, ty, sl);
+        const int x0 = max(stx * 8, b.px0), x1 = min(stx * 8 + 7, b.px1), y0 = max(sty * 8, b.py0), y1 = min(sty * 8 + 7, b.py1);
+#pragma unroll
         for (int idx = lane; idx < 64; idx += 32) {
-          const int px = tx * 8 + (idx & 7), py = ty * 8 + (idx >> 3);
-          if (px >= x0 && px <= x1 && py >= y0 && py <= y1) rtri_pixel(b, px, py, S, vis);
+          const int px = stx * 8 + (idx & 7), py = sty * 8 + (idx >> 3);
+          if (px >= x0 && px <= x1 && py >= y0 && py <= y1) rtri_pixel(b, px, py, S, vis, simple);
         }
       }
     }
@@ -258,8 +274,8 @@ __global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
       rtri_make(q, p.S, static_cast<uint32_t>(fi) * 2u + 1u, t1);
     }
   }
-  rtri_raster(t0, p.S, vis, lane);
-  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane);
+  rtri_raster(t0, p.S, vis, lane, p.simple);
+  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane, p.simple);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -370,13 +386,79 @@ __global__ void __launch_bounds__(128) resolve_kernel(const ResolveParams p) {
   p.mask_depth[o] = am[0] > 0.5f ? 1.f : 0.f;
 }
 
+// SimpleRenderer read-back (moderngl_renderer.py:128-146 + shaders/simple.fsh) of ONE mesh per sample: colour = raw texture
+// colour, alpha = 0 on back faces and where the interpolated edge flag exceeds 0.999, depth = linearised z-buffer value
+// (cleared to 1 -> `far` where nothing was drawn), mask = alpha > 0.5; rows flipped like np.flip(pixels, axis=0).
+__global__ void __launch_bounds__(128) simple_resolve_kernel(const ResolveParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (pix >= p.S * p.S) return;
+  const int px = pix % p.S, py = pix / p.S;
+  const float* mvp = p.mvp + b * 16;
+  const unsigned long long key = p.vis[static_cast<size_t>(b) * p.S * p.S + pix];
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  float depth = 1.0f;
+  if (key != ~0ull) {
+    depth = __uint_as_float(static_cast<uint32_t>(key >> 32));
+    const uint32_t prim = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+    const uint32_t f = prim >> 1, sub = prim & 1u;
+    const ViewRef vr = p.views[b];
+    WVtx in[3], poly[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[f * 3 + k], mvp, in[k]);
+    clip_near(in, poly);
+    WVtx tv[3];
+    tv[0] = poly[0];
+    tv[1] = sub ? poly[2] : poly[1];
+    tv[2] = sub ? poly[3] : poly[2];
+    TriSetup t;
+    tri_setup(tv, p.S, t);
+    float l0, l1, l2;
+    if (t.area > 0 && tri_eval(t, px, py, l0, l1, l2)) {
+      const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
+      const float bs = (b0 + b1) + b2;
+      const float c0 = b0 / bs, c1 = b1 / bs, c2 = b2 / bs;
+      const float uu = (c0 * tv[0].uv[0] + c1 * tv[1].uv[0]) + c2 * tv[2].uv[0];
+      const float vv = (c0 * tv[0].uv[1] + c1 * tv[1].uv[1]) + c2 * tv[2].uv[1];
+      const float edge = (c0 * tv[0].edge + c1 * tv[1].edge) + c2 * tv[2].edge;
+      int tx = static_cast<int>(floorf(uu * static_cast<float>(p.T))), ty = static_cast<int>(floorf(vv * static_cast<float>(p.T)));
+      tx = min(max(tx, 0), p.T - 1); ty = min(max(ty, 0), p.T - 1);
+      const float* tc = vr.tex + (static_cast<size_t>(ty) * p.T + tx) * 3;
+      c[0] = tc[0]; c[1] = tc[1]; c[2] = tc[2];
+      c[3] = edge > 0.999f ? 0.f : 1.f;
+    }
+  }
+  const size_t o = (static_cast<size_t>(b) * p.S + (p.S - 1 - py)) * p.S + px;
+  p.color[o * 3 + 0] = c[0]; p.color[o * 3 + 1] = c[1]; p.color[o * 3 + 2] = c[2];
+  p.depth[o] = p.nf_f / (p.far_f - depth * p.fn_f);
+  p.mask_color[o] = c[3] > 0.5f ? 1.f : 0.f;
+}
+
+// forward_backward_warp, between the two renders (utils.py:385-387): the resolved 8-bit colour becomes the float32 texture of
+// the second mesh (color1 = LANCZOS(to8b(color)) / 255.0, cast by color_texture.write), depth1 = depth[off::ssaa, off::ssaa].
+__global__ void fbw_mid_kernel(const unsigned char* __restrict__ col8, const float* __restrict__ depth, int n, int S, int ssaa,
+                               float* __restrict__ tex, size_t tex_stride, float* __restrict__ d1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= n * n) return;
+  const int y = idx / n, x = idx % n;
+  const int off = (ssaa - 1) / 2;
+  const unsigned char* c8 = col8 + (static_cast<size_t>(b) * n * n + idx) * 3;
+  float* t = tex + b * tex_stride + static_cast<size_t>(idx) * 3;
+  for (int c = 0; c < 3; ++c) t[c] = static_cast<float>(static_cast<double>(c8[c]) / 255.0);
+  d1[static_cast<size_t>(b) * n * n + idx] = depth[static_cast<size_t>(b) * S * S + static_cast<size_t>(y * ssaa + off) * S + (x * ssaa + off)];
+}
+
 // ----------------------------------------------------------------------------------------------------------------------
-// mesh construction (depth_to_mesh with padding='frustum', cal_normal=True), one thread per padded-grid vertex / cell
+// mesh construction (depth_to_mesh, cal_normal=True), one thread per grid vertex / cell.  pad = 1: the grid is padded by one
+// 'edge' ring ((n+2)^2 vertices; padding='frustum' or numeric); pad = 0: padding=None, n^2 vertices.
 // ----------------------------------------------------------------------------------------------------------------------
 struct MeshParams {
   const float* rgbd;          // [B][4][n][n] model space [-1,1]   (lin_depth_in == nullptr)
   const float* lin_depth_in;  // [B][n][n] already linearised depth (numpy-facing depth_to_mesh), or nullptr
-  int B, n;                   // n = image size (128); grid is (n+2)^2
+  int B, n;                   // n = image size (128); grid is (n + 2*pad)^2
+  int pad;                    // 1: one ring of 'edge' padding (padding='frustum' / numeric), 0: padding=None
+  const float* tex_in;        // optional [B][n][n][3] colour texture already in [0,1] (lin_depth_in path)
   float near_f, far_f;        // linearize_depth planes (float32 casts)
   float fn_f, nf_f;           // (far-near), near*far as float32
   double focal, step;         // 0.5/tan(fov/2), plane/n (frustum) or (padding*plane)/n
@@ -420,12 +502,12 @@ __device__ __forceinline__ void cam_point(const MeshParams& p, int b, int r, int
 
 // stage 1: padded points (+frustum ring), padded depth, normals, texture
 __global__ void mesh_points_kernel(const MeshParams p) {
-  const int m = p.n + 2;
+  const int m = p.n + 2 * p.pad;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (idx >= m * m) return;
   const int R = idx / m, C = idx % m;
-  const int r = min(max(R - 1, 0), p.n - 1), c = min(max(C - 1, 0), p.n - 1);     // 'edge' padding
+  const int r = min(max(R - p.pad, 0), p.n - 1), c = min(max(C - p.pad, 0), p.n - 1);     // 'edge' padding
   double pt[3];
   cam_point(p, b, r, c, pt);
   const float dz = lin_depth(p, b, r, c);
@@ -448,11 +530,13 @@ __global__ void mesh_points_kernel(const MeshParams p) {
   for (int j = 0; j < 3; ++j) nv[j] /= nl;
   // frustum ring (utils.py:190-199), in the reference's statement order
   const double dzd = static_cast<double>(dz);
-  if (R == 0) pt[1] += p.step * dzd;
-  if (R == m - 1) pt[1] -= p.step * dzd;
-  if (C == 0) pt[0] -= p.step * dzd;
-  if (C == m - 1) pt[0] += p.step * dzd;
-  if (p.frustum) {
+  if (p.pad) {
+    if (R == 0) pt[1] += p.step * dzd;
+    if (R == m - 1) pt[1] -= p.step * dzd;
+    if (C == 0) pt[0] -= p.step * dzd;
+    if (C == m - 1) pt[0] += p.step * dzd;
+  }
+  if (p.pad && p.frustum) {
     if (R == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
     if (R == m - 1) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
     if (C == 0) { const double s = -0.1 / pt[2]; pt[0] *= s; pt[1] *= s; pt[2] *= s; }
@@ -462,15 +546,19 @@ __global__ void mesh_points_kernel(const MeshParams p) {
   for (int j = 0; j < 3; ++j) { p.pts[o * 3 + j] = pt[j]; p.nrm[o * 3 + j] = nv[j]; }
   p.dep[o] = dz;
   p.disc[o] = 0;
-  if (p.rgbd != nullptr && R >= 1 && R <= p.n && C >= 1 && C <= p.n) {
+  if (R >= p.pad && R < p.n + p.pad && C >= p.pad && C < p.n + p.pad) {
     float* t = p.tex + b * p.tex_stride + (static_cast<size_t>(r) * p.n + c) * 3;
-    for (int j = 0; j < 3; ++j) t[j] = p.rgbd[((static_cast<size_t>(b) * 4 + j) * p.n + r) * p.n + c] * 0.5f + 0.5f;
+    if (p.rgbd != nullptr) {
+      for (int j = 0; j < 3; ++j) t[j] = p.rgbd[((static_cast<size_t>(b) * 4 + j) * p.n + r) * p.n + c] * 0.5f + 0.5f;
+    } else if (p.tex_in != nullptr) {
+      for (int j = 0; j < 3; ++j) t[j] = p.tex_in[((static_cast<size_t>(b) * p.n + r) * p.n + c) * 3 + j];
+    }
   }
 }
 
 // stage 2: per grid cell — diagonal choice, two faces, discontinuity marking (utils.py:113-141, 213-218)
 __global__ void mesh_faces_kernel(const MeshParams p) {
-  const int m = p.n + 2, q = m - 1;
+  const int m = p.n + 2 * p.pad, q = m - 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (idx >= q * q) return;
@@ -501,7 +589,7 @@ __global__ void mesh_faces_kernel(const MeshParams p) {
 
 // stage 3: erosion flags, world transform, float32 vertex buffer (utils.py:232-258, moderngl_renderer.py:284-289)
 __global__ void mesh_verts_kernel(const MeshParams p) {
-  const int m = p.n + 2;
+  const int m = p.n + 2 * p.pad;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (idx >= m * m) return;
@@ -517,7 +605,7 @@ __global__ void mesh_verts_kernel(const MeshParams p) {
         if (rr >= 0 && rr < m && cc >= 0 && cc < m && disc[rr * m + cc]) { ero = 1; break; }
       }
   }
-  const int ring = (R == 0 || R == m - 1 || C == 0 || C == m - 1) ? 1 : 0;
+  const int ring = (p.pad && (R == 0 || R == m - 1 || C == 0 || C == m - 1)) ? 1 : 0;
   const int flag = disc[idx] + 2 * ring + 4 * ero;
   const float* M = p.inv_mv + b * 16;
   const double* pt = p.pts + (base + idx) * 3;
@@ -531,7 +619,7 @@ __global__ void mesh_verts_kernel(const MeshParams p) {
                       static_cast<double>(M[r * 4 + 2]) * nv[2];
     o[3 + r] = static_cast<float>(nn);
   }
-  const int r0 = min(max(R - 1, 0), p.n - 1), c0 = min(max(C - 1, 0), p.n - 1);
+  const int r0 = min(max(R - p.pad, 0), p.n - 1), c0 = min(max(C - p.pad, 0), p.n - 1);
   o[6] = static_cast<float>(lin_uv(p, c0));
   o[7] = static_cast<float>(lin_uv(p, r0));
   o[8] = static_cast<float>(flag);
@@ -763,40 +851,48 @@ class Warp {
   float* tex_slot(int b, int v) { return tex_ + (static_cast<size_t>(b) * maxv_ + v) * n_ * n_ * 3; }
 
   // sample.py:126-138 for every sample of the batch: colors.append(rgb), meshes.append(depth_to_mesh(...))
-  // numpy-facing depth_to_mesh: linear depth in, vertex buffer + faces out (slot 0 of a scratch view is used)
+  // numpy-facing depth_to_mesh: linear depth in, vertex buffer + faces out (the last view slot is used as scratch).
+  // wp.padding: 0 = 'frustum', > 0 = that many pixels, < 0 = None (no ring: n^2 vertices, 2*(n-1)^2 faces).
   void mesh_from_depth(const float* lin_depth_host, const float* mv_host, const ivid_warp_params_t& wp, float* verts_host,
                        uint32_t* faces_host, cudaStream_t st) {
     IVID_REQUIRE(B_ == 1, "mesh_from_depth works on single-sample renderers");
+    IVID_CHECK_CUDA(cudaSetDevice(device_));
     float* d_in = nullptr;
     IVID_CHECK_CUDA(cudaMalloc(&d_in, static_cast<size_t>(n_) * n_ * 4));
     IVID_CHECK_CUDA(cudaMemcpy(d_in, lin_depth_host, static_cast<size_t>(n_) * n_ * 4, cudaMemcpyHostToDevice));
-    const int saved = nviews_;
-    nviews_ = maxv_ - 1;                      // build into the last slot, then restore the live view count
+    const int pad = wp.padding < 0.0 ? 0 : 1;
+    const int m = n_ + 2 * pad;
     try {
-      add_view_impl(nullptr, d_in, mv_host, true, wp, st);
-    } catch (...) { nviews_ = saved; cudaFree(d_in); throw; }
-    IVID_CHECK_CUDA(cudaMemcpy(verts_host, verts_slot(0, maxv_ - 1), static_cast<size_t>(V_) * 9 * 4, cudaMemcpyDeviceToHost));
-    IVID_CHECK_CUDA(cudaMemcpy(faces_host, faces_slot(0, maxv_ - 1), static_cast<size_t>(F_) * 3 * 4, cudaMemcpyDeviceToHost));
-    nviews_ = saved;
+      build_mesh(maxv_ - 1, nullptr, d_in, nullptr, mv_host, true, wp, st);
+    } catch (...) { cudaFree(d_in); throw; }
+    IVID_CHECK_CUDA(cudaMemcpy(verts_host, verts_slot(0, maxv_ - 1), static_cast<size_t>(m) * m * 9 * 4, cudaMemcpyDeviceToHost));
+    IVID_CHECK_CUDA(cudaMemcpy(faces_host, faces_slot(0, maxv_ - 1), static_cast<size_t>(2) * (m - 1) * (m - 1) * 3 * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_in);
   }
   void add_view(const float* rgbd_dev, const float* mv_host, bool shared, const ivid_warp_params_t& wp, cudaStream_t st) {
-    add_view_impl(rgbd_dev, nullptr, mv_host, shared, wp, st);
-  }
-  void add_view_impl(const float* rgbd_dev, const float* lin_depth_dev, const float* mv_host, bool shared,
-                     const ivid_warp_params_t& wp, cudaStream_t st) {
     IVID_REQUIRE(nviews_ < maxv_, "more source views than max_views");
+    IVID_REQUIRE(wp.padding >= 0.0, "add_view: source views of the aggregation renderer are padded meshes");
+    build_mesh(nviews_, rgbd_dev, nullptr, nullptr, mv_host, shared, wp, st);
+    ++nviews_;
+    views_dirty_ = true;
+  }
+  // depth_to_mesh for every sample of the batch into view slot `slot` (utils.py:144-260); the depth comes either from the
+  // model-space RGBD (rgbd_dev, sampling loop) or from an already linearised depth image (lin_depth_dev [+ tex_in_dev]).
+  void build_mesh(int slot, const float* rgbd_dev, const float* lin_depth_dev, const float* tex_in_dev, const float* mv_host,
+                  bool shared, const ivid_warp_params_t& wp, cudaStream_t st) {
+    IVID_REQUIRE(slot >= 0 && slot < maxv_, "view slot out of range");
     IVID_CHECK_CUDA(cudaSetDevice(device_));
     std::vector<float> inv(B_ * 16);
     for (int b = 0; b < B_; ++b) {
       const float* mv = mv_host + (shared ? 0 : b * 16);
       mat4_inverse(mv, inv.data() + b * 16);
-      float* cam = cams_.data() + (static_cast<size_t>(b) * maxv_ + nviews_) * 3;
+      float* cam = cams_.data() + (static_cast<size_t>(b) * maxv_ + slot) * 3;
       cam[0] = inv[b * 16 + 3]; cam[1] = inv[b * 16 + 7]; cam[2] = inv[b * 16 + 11];     // inverse(modelview)[3] (column 3)
     }
     IVID_CHECK_CUDA(cudaMemcpyAsync(inv_dev_, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice, st));
     MeshParams p;
-    p.rgbd = rgbd_dev; p.lin_depth_in = lin_depth_dev; p.B = B_; p.n = n_;
+    p.rgbd = rgbd_dev; p.lin_depth_in = lin_depth_dev; p.tex_in = tex_in_dev; p.B = B_; p.n = n_;
+    p.pad = wp.padding < 0.0 ? 0 : 1;
     p.near_f = static_cast<float>(wp.near); p.far_f = static_cast<float>(wp.far);
     p.fn_f = static_cast<float>(wp.far - wp.near);
     p.nf_f = static_cast<float>(wp.near * wp.far);
@@ -813,18 +909,16 @@ class Warp {
     p.erode_k = wp.erode_rgb > 0 ? 2 * wp.erode_rgb + 1 : 0;
     p.inv_mv = inv_dev_;
     p.pts = pts_; p.nrm = nrm_; p.dep = dep_; p.disc = disc_;
-    p.verts = verts_slot(0, nviews_); p.faces = faces_slot(0, nviews_); p.tex = tex_slot(0, nviews_);
+    p.verts = verts_slot(0, slot); p.faces = faces_slot(0, slot); p.tex = tex_slot(0, slot);
     p.verts_stride = static_cast<size_t>(maxv_) * V_ * 9; p.faces_stride = static_cast<size_t>(maxv_) * F_ * 3;
     p.tex_stride = static_cast<size_t>(maxv_) * n_ * n_ * 3;
-    const int m = n_ + 2;
+    const int m = n_ + 2 * p.pad;
     dim3 gv((m * m + 127) / 128, B_), gf(((m - 1) * (m - 1) + 127) / 128, B_);
     mesh_points_kernel<<<gv, 128, 0, st>>>(p);
     mesh_faces_kernel<<<gf, 128, 0, st>>>(p);
     mesh_verts_kernel<<<gv, 128, 0, st>>>(p);
     IVID_CHECK_CUDA(cudaGetLastError());
     IVID_CHECK_CUDA(cudaStreamSynchronize(st));     // inv is a host temporary
-    ++nviews_;
-    views_dirty_ = true;
   }
 
   void set_mesh(int b, int v, const float* verts_host, const uint32_t* faces_host, const float* color_host, const float* mv_host) {
@@ -840,6 +934,21 @@ class Warp {
     nviews_ = std::max(nviews_, v + 1);
     views_dirty_ = true;
   }
+  // raw upload of a grid mesh with explicit sizes (SimpleRenderer meshes may be unpadded)
+  void upload_mesh(int b, int v, const float* verts_host, int nverts, const uint32_t* faces_host, int nfaces, const float* color_host) {
+    IVID_REQUIRE(b >= 0 && b < B_ && v >= 0 && v < maxv_ && nverts <= V_ && nfaces <= F_, "upload_mesh: out of range");
+    IVID_CHECK_CUDA(cudaSetDevice(device_));
+    IVID_CHECK_CUDA(cudaMemcpy(verts_slot(b, v), verts_host, static_cast<size_t>(nverts) * 9 * 4, cudaMemcpyHostToDevice));
+    IVID_CHECK_CUDA(cudaMemcpy(faces_slot(b, v), faces_host, static_cast<size_t>(nfaces) * 3 * 4, cudaMemcpyHostToDevice));
+    IVID_CHECK_CUDA(cudaMemcpy(tex_slot(b, v), color_host, static_cast<size_t>(n_) * n_ * 3 * 4, cudaMemcpyHostToDevice));
+  }
+  void download_raw(float* color, float* depth, float* mask, cudaStream_t st) {
+    const size_t px = static_cast<size_t>(B_) * S_ * S_;
+    IVID_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (color) IVID_CHECK_CUDA(cudaMemcpy(color, raw_color_, px * 12, cudaMemcpyDeviceToHost));
+    if (depth) IVID_CHECK_CUDA(cudaMemcpy(depth, raw_depth_, px * 4, cudaMemcpyDeviceToHost));
+    if (mask) IVID_CHECK_CUDA(cudaMemcpy(mask, raw_mc_, px * 4, cudaMemcpyDeviceToHost));
+  }
   void get_mesh(int b, int v, float* verts_host, uint32_t* faces_host, float* color_host) {
     IVID_REQUIRE(b >= 0 && b < B_ && v >= 0 && v < nviews_, "get_mesh: slot out of range");
     IVID_CHECK_CUDA(cudaSetDevice(device_));
@@ -854,7 +963,23 @@ class Warp {
     IVID_REQUIRE(nviews_ >= 1, "render: no source views");
     IVID_CHECK_CUDA(cudaSetDevice(device_));
     upload_views(st);
-    // glm::perspective(radians(fov), 1, near, far) in float32, P*MV in double -> float32
+    upload_mvp(target_mv_host, shared, fov_deg, st);
+    // visibility buffers are stored [B][nviews][S*S] contiguously for the live view count
+    IVID_CHECK_CUDA(cudaMemsetAsync(vis_, 0xFF, static_cast<size_t>(B_) * nviews_ * S_ * S_ * 8, st));
+    RasterParams rp;
+    rp.views = views_dev_; rp.mvp = mvp_dev_; rp.vis = vis_; rp.nviews = nviews_; rp.F = F_; rp.S = S_; rp.simple = 0;
+    dim3 gr((F_ + 127) / 128, nviews_, B_);
+    raster_kernel<<<gr, 128, 0, st>>>(rp);
+    ResolveParams sp;
+    sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = nviews_; sp.S = S_; sp.T = n_;
+    sp.nf_f = static_cast<float>(near_ * far_); sp.far_f = static_cast<float>(far_); sp.fn_f = static_cast<float>(far_ - near_);
+    sp.color = raw_color_; sp.depth = raw_depth_; sp.mask_color = raw_mc_; sp.mask_depth = raw_md_;
+    dim3 gs((S_ * S_ + 127) / 128, B_);
+    resolve_kernel<<<gs, 128, 0, st>>>(sp);
+    IVID_CHECK_CUDA(cudaGetLastError());
+  }
+  // P*MV of the target view(s): glm::perspective(radians(fov), 1, near, far) in float32, product in double -> float32
+  void upload_mvp(const float* target_mv_host, bool shared, double fov_deg, cudaStream_t st) {
     const float t = std::tan(static_cast<float>(fov_deg * (M_PI / 180.0)) / 2.0f);
     const float nf = static_cast<float>(near_), ff = static_cast<float>(far_);
     double P[16] = {0};
@@ -872,20 +997,66 @@ class Warp {
     }
     IVID_CHECK_CUDA(cudaMemcpyAsync(mvp_dev_, mvp.data(), mvp.size() * 4, cudaMemcpyHostToDevice, st));
     IVID_CHECK_CUDA(cudaStreamSynchronize(st));
-    // visibility buffers are stored [B][nviews][S*S] contiguously for the live view count
-    IVID_CHECK_CUDA(cudaMemsetAsync(vis_, 0xFF, static_cast<size_t>(B_) * nviews_ * S_ * S_ * 8, st));
+  }
+
+  // SimpleRenderer.render(mesh, color, modelview, fov) (moderngl_renderer.py:94-146) of the mesh in view slot `slot` of every
+  // sample (faces of an n + 2*pad grid) -> raw_color_ / raw_depth_ / raw_mc_ (mask = alpha > 0.5) at render size.
+  void render_simple(int slot, int pad, const float* target_mv_host, bool shared, double fov_deg, cudaStream_t st) {
+    IVID_REQUIRE(slot >= 0 && slot < maxv_, "render_simple: view slot out of range");
+    IVID_CHECK_CUDA(cudaSetDevice(device_));
+    std::vector<ViewRef> refs(static_cast<size_t>(B_));
+    for (int b = 0; b < B_; ++b) {
+      ViewRef& r = refs[b];
+      r.verts = verts_slot(b, slot); r.faces = faces_slot(b, slot); r.tex = tex_slot(b, slot);
+      r.cam[0] = r.cam[1] = r.cam[2] = 0.f;
+    }
+    IVID_CHECK_CUDA(cudaMemcpyAsync(views_dev_, refs.data(), refs.size() * sizeof(ViewRef), cudaMemcpyHostToDevice, st));
+    views_dirty_ = true;       // the aggregation renderer's table was overwritten
+    upload_mvp(target_mv_host, shared, fov_deg, st);
+    IVID_CHECK_CUDA(cudaMemsetAsync(vis_, 0xFF, static_cast<size_t>(B_) * S_ * S_ * 8, st));
+    const int m = n_ + 2 * pad;
     RasterParams rp;
-    rp.views = views_dev_; rp.mvp = mvp_dev_; rp.vis = vis_; rp.nviews = nviews_; rp.F = F_; rp.S = S_;
-    dim3 gr((F_ + 127) / 128, nviews_, B_);
+    rp.views = views_dev_; rp.mvp = mvp_dev_; rp.vis = vis_; rp.nviews = 1; rp.F = 2 * (m - 1) * (m - 1); rp.S = S_; rp.simple = 1;
+    dim3 gr((rp.F + 127) / 128, 1, B_);
     raster_kernel<<<gr, 128, 0, st>>>(rp);
     ResolveParams sp;
-    sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = nviews_; sp.S = S_; sp.T = n_;
+    sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = 1; sp.S = S_; sp.T = n_;
     sp.nf_f = static_cast<float>(near_ * far_); sp.far_f = static_cast<float>(far_); sp.fn_f = static_cast<float>(far_ - near_);
     sp.color = raw_color_; sp.depth = raw_depth_; sp.mask_color = raw_mc_; sp.mask_depth = raw_md_;
     dim3 gs((S_ * S_ + 127) / 128, B_);
-    resolve_kernel<<<gs, 128, 0, st>>>(sp);
+    simple_resolve_kernel<<<gs, 128, 0, st>>>(sp);
     IVID_CHECK_CUDA(cudaGetLastError());
   }
+
+  // forward_backward_warp (utils.py:335-417) for every sample of the batch: view-0 RGBD -> mesh (wp.padding) -> rendered at
+  // view 1 -> resolved (8-bit LANCZOS colour, point-sampled depth) -> re-meshed without padding, with the discontinuity
+  // test -> rendered back at view 0 -> resolve, project_depth, 7-of-9 mask vote, depth_edge, products.
+  //   lin_depth0_dev [B][n][n] linearised view-0 depth, color0_dev [B][n][n][3] in [0,1]; out_dev [B][7][n][n] =
+  //   color(3) depth mask mask mask-less-projected-depth (same layout as aggregate_conditions; rows 4 and 5 are both `mask`).
+  void forward_backward(const float* lin_depth0_dev, const float* color0_dev, const float* mv1_host, const float* mv0_host, bool shared,
+                        const ivid_warp_params_t& wp, float* out_dev, cudaStream_t st) {
+    IVID_REQUIRE(maxv_ >= 2, "forward_backward_warp needs two view slots");
+    IVID_REQUIRE((S_ / n_) % 2 == 1 || S_ == n_, "forward_backward_warp: odd super-sampling factor");
+    ivid_warp_params_t w0 = wp;
+    w0.atol = -1.0; w0.rtol = -1.0; w0.erode_rgb = 0;                 // mesh0: atol = rtol = None (utils.py:378-379)
+    build_mesh(0, nullptr, lin_depth0_dev, color0_dev, mv0_host, shared, w0, st);
+    render_simple(0, wp.padding < 0.0 ? 0 : 1, mv1_host, shared, wp.fov_deg, st);
+    PostParams pp = post_params(raw_color_, raw_depth_, raw_mc_, raw_mc_, wp, nullptr);
+    dim3 gh((S_ * n_ + 127) / 128, B_), gn((n_ * n_ + 127) / 128, B_);
+    lanczos_h_kernel<<<gh, 128, 0, st>>>(pp);
+    lanczos_v_kernel<<<gn, 128, 0, st>>>(pp);
+    fbw_mid_kernel<<<gn, 128, 0, st>>>(col8_, raw_depth_, n_, S_, S_ / n_, tex_slot(0, 1), static_cast<size_t>(maxv_) * n_ * n_ * 3, dproj_);
+    IVID_CHECK_CUDA(cudaGetLastError());
+    ivid_warp_params_t w1 = wp;
+    w1.padding = -1.0; w1.erode_rgb = 0;                              // mesh1: padding=None, atol / rtol as given
+    build_mesh(1, nullptr, dproj_, nullptr, mv1_host, shared, w1, st);
+    render_simple(1, 0, mv0_host, shared, wp.fov_deg, st);
+    ivid_warp_params_t wpost = wp;
+    wpost.erode_rgb = 1;                                              // no erosion: mask_rgb == mask
+    post(raw_color_, raw_depth_, raw_mc_, raw_mc_, wpost, out_dev, st);
+    nviews_ = 0;
+  }
+
   void copy_raw(float* color, float* depth, float* mc, float* md, cudaStream_t st) {
     const size_t px = static_cast<size_t>(B_) * S_ * S_;
     if (color) IVID_CHECK_CUDA(cudaMemcpyAsync(color, raw_color_, px * 12, cudaMemcpyDeviceToDevice, st));
@@ -899,9 +1070,8 @@ class Warp {
     render(target_mv_host, shared, wp.fov_deg, st);
     post(raw_color_, raw_depth_, raw_mc_, raw_md_, wp, out_dev, st);
   }
-  void post(const float* color, const float* depth, const float* mc, const float* md, const ivid_warp_params_t& wp, float* out_dev,
-            cudaStream_t st) {
-    IVID_REQUIRE(wp.erode_rgb >= 1, "aggregate_conditions: erode_rgb must be >= 1");
+  PostParams post_params(const float* color, const float* depth, const float* mc, const float* md, const ivid_warp_params_t& wp,
+                         float* out_dev) {
     PostParams p;
     p.color = color; p.depth = depth; p.mask_color = mc; p.mask_depth = md;
     p.B = B_; p.S = S_; p.n = n_; p.ssaa = S_ / n_;
@@ -912,6 +1082,12 @@ class Warp {
     p.atol_f = static_cast<float>(wp.atol < 0.0 ? 0.0 : wp.atol); p.rtol_f = static_cast<float>(wp.rtol < 0.0 ? 0.0 : wp.rtol);
     p.erode_k = 2 * wp.erode_rgb - 1;
     p.tmp8 = tmp8_; p.col8 = col8_; p.dproj = dproj_; p.m0 = m0_; p.mr0 = mr0_; p.out = out_dev;
+    return p;
+  }
+  void post(const float* color, const float* depth, const float* mc, const float* md, const ivid_warp_params_t& wp, float* out_dev,
+            cudaStream_t st) {
+    IVID_REQUIRE(wp.erode_rgb >= 1, "aggregate_conditions: erode_rgb must be >= 1");
+    PostParams p = post_params(color, depth, mc, md, wp, out_dev);
     dim3 gh((S_ * n_ + 127) / 128, B_), gn((n_ * n_ + 127) / 128, B_);
     lanczos_h_kernel<<<gh, 128, 0, st>>>(p);
     lanczos_v_kernel<<<gn, 128, 0, st>>>(p);
@@ -1051,6 +1227,45 @@ int ivid_warp_aggregate(ivid_warp_t* w, const float* target_mv_host, int shared_
   return warp_guard([&] {
     IVID_REQUIRE(w && target_mv_host && params && cond_dev, "aggregate: NULL argument");
     w->impl->aggregate(target_mv_host, shared_modelview != 0, *params, cond_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+int ivid_warp_render_simple(ivid_warp_t* w, const float* verts_host, int nverts, const uint32_t* faces_host, int nfaces,
+                            const float* color_host, const float* target_mv_host, double fov_deg, float* color_out_host,
+                            float* depth_out_host, float* mask_out_host, void* stream) {
+  return warp_guard([&] {
+    IVID_REQUIRE(w && verts_host && faces_host && color_host && target_mv_host, "render_simple: NULL argument");
+    Warp& W = *w->impl;
+    IVID_REQUIRE(W.batch() == 1, "render_simple works on single-sample renderers");
+    const int n = W.image_size();
+    const int pad = nverts == (n + 2) * (n + 2) ? 1 : 0;
+    const int m = n + 2 * pad;
+    IVID_REQUIRE(nverts == m * m && nfaces == 2 * (m - 1) * (m - 1), "render_simple: the mesh must be an n x n or (n+2) x (n+2) grid mesh");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    W.upload_mesh(0, 0, verts_host, nverts, faces_host, nfaces, color_host);
+    W.render_simple(0, pad, target_mv_host, true, fov_deg, st);
+    W.download_raw(color_out_host, depth_out_host, mask_out_host, st);
+  });
+}
+int ivid_warp_forward_backward(ivid_warp_t* w, const float* lin_depth0_host, const float* color0_host, const float* mv1_host,
+                               const float* mv0_host, int shared_modelview, const ivid_warp_params_t* params, float* out_host,
+                               void* stream) {
+  return warp_guard([&] {
+    IVID_REQUIRE(w && lin_depth0_host && color0_host && mv1_host && mv0_host && params && out_host, "forward_backward: NULL argument");
+    Warp& W = *w->impl;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t px = static_cast<size_t>(W.batch()) * W.image_size() * W.image_size();
+    float *d_lin = nullptr, *d_col = nullptr, *d_out = nullptr;
+    IVID_CHECK_CUDA(cudaMalloc(&d_lin, px * 4));
+    IVID_CHECK_CUDA(cudaMalloc(&d_col, px * 12));
+    IVID_CHECK_CUDA(cudaMalloc(&d_out, px * 28));
+    try {
+      IVID_CHECK_CUDA(cudaMemcpyAsync(d_lin, lin_depth0_host, px * 4, cudaMemcpyHostToDevice, st));
+      IVID_CHECK_CUDA(cudaMemcpyAsync(d_col, color0_host, px * 12, cudaMemcpyHostToDevice, st));
+      W.forward_backward(d_lin, d_col, mv1_host, mv0_host, shared_modelview != 0, *params, d_out, st);
+      IVID_CHECK_CUDA(cudaMemcpyAsync(out_host, d_out, px * 28, cudaMemcpyDeviceToHost, st));
+      IVID_CHECK_CUDA(cudaStreamSynchronize(st));
+    } catch (...) { cudaFree(d_lin); cudaFree(d_col); cudaFree(d_out); throw; }
+    cudaFree(d_lin); cudaFree(d_col); cudaFree(d_out);
   });
 }
 int ivid_warp_postfilter(ivid_warp_t* w, const float* color_dev, const float* depth_dev, const float* mask_color_dev,

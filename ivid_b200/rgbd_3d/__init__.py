@@ -1,3 +1,3 @@
-from .renderer import AggregationRenderer, DeviceWarp
+from .renderer import AggregationRenderer, SimpleRenderer, DeviceWarp
 from . import utils
 from . import glm_compat

@@ -13,11 +13,12 @@ from .. import _lib
 from ..utils import edict
 from .glm_compat import as_matrix
 
-__all__ = ["AggregationRenderer", "DeviceWarp", "warp_params"]
+__all__ = ["AggregationRenderer", "SimpleRenderer", "DeviceWarp", "warp_params"]
 
 
 def warp_params(fov=45, near=0.5, far=100, atol=0.02, rtol=0.02, erode_rgb=2, padding=0.0) -> _lib.WarpParamsT:
-    """padding: 0 = 'frustum' (sampling path), > 0 = numeric padding in pixels (free-view rendering, load_scene)."""
+    """padding: 0 = 'frustum' (sampling path), > 0 = numeric padding in pixels (free-view rendering, load_scene; the
+    training-pair warp), < 0 = None (no padding ring)."""
     p = _lib.WarpParamsT()
     p.padding = float(padding)
     p.fov_deg, p.near, p.far = float(fov), float(near), float(far)
@@ -109,6 +110,49 @@ class AggregationRenderer(_Native):
         assert cur.value >= n, "render: meshes were not uploaded (is_autoregressive=True needs every view rendered once)"
         if cur.value != n:
             raise AssertionError(f"renderer holds {cur.value} views but {n} meshes were passed; create a new renderer per sample")
+
+
+class SimpleRenderer(_Native):
+    """Renderer of one textured grid mesh with raw texture colours (reference moderngl_renderer.py:11-148 + shaders/simple.*):
+    alpha = 0 on back faces and discontinuity edges.  Used by rgbd_3d.utils.forward_backward_warp (training-pair synthesis,
+    datasets/base.py:219).  Same constructor and .render() contract as the reference class; numpy HWC in / out."""
+
+    def __init__(self, render_size=128, image_size=128, near=0.01, far=200.0, device=0):
+        super().__init__(image_size, render_size, 2, 1, near, far, device)
+
+    def render(self, mesh, color, modelview, fov=45.0):
+        L = _lib.lib()
+        v = mesh.vertices if hasattr(mesh, "vertices") else mesh["vertices"]
+        pos = np.asarray(v["position"], np.float32)
+        nrm = np.asarray(v["normal"], np.float32) if "normal" in v else np.tile(np.float32([0, 0, 1]), (pos.shape[0], 1))
+        vb = np.ascontiguousarray(np.concatenate([pos, nrm, np.asarray(v["uv"], np.float32), np.asarray(v["flag"], np.float32)], axis=-1))
+        faces = np.ascontiguousarray(np.asarray(mesh.faces if hasattr(mesh, "faces") else mesh["faces"]).astype(np.uint32))
+        col = np.ascontiguousarray(np.asarray(color).astype(np.float32))
+        S = self.render_size
+        targets = modelview if isinstance(modelview, list) else [modelview]
+        ret = []
+        for t in targets:
+            c = np.empty((S, S, 3), np.float32); d = np.empty((S, S, 1), np.float32); m = np.empty((S, S, 1), np.float32)
+            tm = _mv(t)
+            with torch.cuda.device(self.device):
+                _lib.check(L.ivid_warp_render_simple(self._handle, vb.ctypes.data, vb.shape[0], faces.ctypes.data, faces.shape[0],
+                                                     col.ctypes.data, tm.ctypes.data, float(fov), c.ctypes.data, d.ctypes.data,
+                                                     m.ctypes.data, self._stream()))
+            ret.append(edict({"color": c, "depth": d, "mask": m > 0.5}))
+        return ret if len(ret) > 1 else ret[0]
+
+    def forward_backward(self, lin_depth0, color0, modelview1, modelview0, padding, fov, near, far, atol, rtol):
+        """The whole forward_backward_warp on the device (one upload, one download); see rgbd_3d.utils.forward_backward_warp."""
+        n = self.image_size
+        d0 = np.ascontiguousarray(np.asarray(lin_depth0, np.float32).reshape(1, n, n))
+        c0 = np.ascontiguousarray(np.asarray(color0, np.float32).reshape(1, n, n, 3))
+        out = np.empty((1, 7, n, n), np.float32)
+        p = warp_params(fov, near, far, atol, rtol, 0, padding=-1.0 if padding is None else (0.0 if padding == "frustum" else float(padding)))
+        m1, m0 = _mv(modelview1), _mv(modelview0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ivid_warp_forward_backward(self._handle, d0.ctypes.data, c0.ctypes.data, m1.ctypes.data, m0.ctypes.data, 1,
+                                                             ctypes.byref(p), out.ctypes.data, self._stream()))
+        return out[0]
 
 
 class DeviceWarp(_Native):

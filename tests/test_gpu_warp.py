@@ -74,7 +74,7 @@ def test_numpy_facing_depth_to_mesh(wg):
     assert np.array_equal(m.faces, ref.faces) and np.array_equal(m.vertices.flag, ref.vertices.flag.astype(np.float32))
     assert np.abs(m.vertices.position - ref.vertices.position).max() < 2.5e-7
     with pytest.raises(NotImplementedError):
-        rgbd_3d.utils.depth_to_mesh(d, padding=None, modelview=wg["views"][1])
+        rgbd_3d.utils.depth_to_mesh(d, padding="bogus", modelview=wg["views"][1])
     # tolerances left at None (the reference's defaults): no discontinuity test at all, hence no erosion either; a single None
     # counts as 0 (utils.py:227-229)
     for at, rt in ((None, None), (0.03, None), (None, 0.03)):
@@ -224,3 +224,49 @@ def test_free_view_render_matches_oracle(wg, tmp_path):
         print(f"[parity] free-view frame {j}: resolved colour pixels off by more than one 8-bit step: {off:.2e}")
         assert off < 1e-3
         assert (d8 != d8r).mean() < 1e-2
+
+
+def test_unpadded_mesh_and_simple_renderer_match_oracle(wg):
+    """depth_to_mesh(padding=None, cal_normal=False) and SimpleRenderer.render (training-pair warp building blocks)."""
+    fov = float(wg["params"][2])
+    d = warp_ref.linearize_depth(wg["rgbd0"][:, :, 3:], 0.5, 100)
+    for pad in (None, 128):
+        m = rgbd_3d.utils.depth_to_mesh(d, padding=pad, fov=fov, modelview=wg["views"][1], atol=0.02, rtol=0.02)
+        ref = warp_ref.depth_to_mesh(d, fov=fov, modelview=wg["views"][1], atol=0.02, rtol=0.02, padding=pad, cal_normal=False)
+        assert "normal" not in m.vertices
+        assert np.array_equal(m.faces, ref.faces) and np.array_equal(m.vertices.flag, ref.vertices.flag.astype(np.float32)), pad
+        assert np.array_equal(m.vertices.uv, ref.vertices.uv.astype(np.float32))
+        pos_ref = ref.vertices.position.astype(np.float32)
+        assert (np.abs(m.vertices.position - pos_ref) <= np.spacing(np.abs(pos_ref))).all(), "positions within one float32 ulp"
+        got = rgbd_3d.SimpleRenderer(384, 128, near=0.1, far=200).render(ref, wg["rgbd0"][:, :, :3], wg["views"][2], fov)
+        want = warp_ref.SoftwareSimpleRenderer(384, 128, near=0.1, far=200).render(ref, wg["rgbd0"][:, :, :3], wg["views"][2], fov)
+        assert np.array_equal(got.mask, want.mask), "coverage / alpha must match the oracle exactly on identical meshes"
+        assert np.array_equal(got.color, want.color.astype(np.float32))
+        dz = np.abs(got.depth - want.depth)
+        print(f"[parity] SimpleRenderer (padding={pad}): mask / colour exact, depth max rel {float((dz / want.depth).max()):.2e}")
+        assert (dz / want.depth).max() < 1e-5
+
+
+def test_forward_backward_warp_matches_oracle_and_golden(wg):
+    """rgbd_3d.utils.forward_backward_warp (datasets/base.py:238 call shape: padding = image_size, near 0.5, far 100) against
+    the oracle pipeline and the fixture produced by the unmodified reference function."""
+    fov = float(wg["params"][2])
+    r = rgbd_3d.utils.forward_backward_warp(rgbd_3d.SimpleRenderer(384, 128, near=0.1, far=200), wg["rgbd0"], wg["views"][2],
+                                            modelview0=wg["views"][0], padding=128, fov=fov, near=0.5, far=100)
+    ref = warp_ref.forward_backward_warp(warp_ref.SoftwareSimpleRenderer(384, 128, near=0.1, far=200), wg["rgbd0"], wg["views"][2],
+                                         modelview0=wg["views"][0], padding=128, fov=fov, near=0.5, far=100)
+    for name, want in (("oracle", ref), ("reference golden", {k: wg[f"fbw_{k}"] for k in ("color", "depth", "mask")})):
+        m_ne = (r.mask != np.asarray(want["mask"], np.float32)).mean()
+        agree = (r.mask == np.asarray(want["mask"], np.float32))[..., 0]
+        dd = np.abs(r.depth - np.asarray(want["depth"], np.float32))[agree].max()
+        dc = np.abs(r.color - np.asarray(want["color"], np.float32))[agree]
+        print(f"[parity] forward_backward_warp vs {name}: mask differs on {m_ne:.2e} of pixels, depth max {dd:.2e}, colour max {dc.max():.4f} "
+              f"({(dc > 1.5 / 255).mean():.2e} off by more than one 8-bit step), kept {float(r.mask.mean()):.3f}")
+        assert m_ne < 1e-3 and dd < 1e-5 and (dc > 1.5 / 255).mean() < 1e-3
+    # size-independent property: warping to the SAME camera and back keeps almost everything and reproduces the input
+    same = rgbd_3d.utils.forward_backward_warp(rgbd_3d.SimpleRenderer(384, 128, near=0.1, far=200), wg["rgbd0"], wg["views"][0],
+                                               modelview0=wg["views"][0], padding=128, fov=fov, near=0.5, far=100)
+    keep = same.mask[..., 0] > 0
+    assert keep.mean() > 0.9
+    assert np.abs(same.depth[..., 0] - wg["rgbd0"][:, :, 3])[keep].max() < 1e-5
+    assert np.quantile(np.abs(same.color - wg["rgbd0"][:, :, :3])[keep], 0.95) <= 2.0 / 255 + 1e-6
