@@ -261,9 +261,12 @@ void attn_launch_destroy(AttnLaunch* l) { delete l; }
 void attn_launch_run(const AttnLaunch* l, cudaStream_t s) {
   static std::once_flag once;
   std::call_once(once, [] {
-    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg::SMEM_BYTES));
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg2::SMEM_BYTES));
   });
-  attention_kernel<<<l->grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
+  static const bool v1 = getenv("IVID_ATTN_V1") != nullptr;      // previous kernel (single-buffered S, 4 CTAs / SM) for same-box A/B
+  if (v1) attention_kernel_v1<<<l->grid, AttnCfg::THREADS, AttnCfg::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
+  else attention_kernel<<<l->grid, AttnCfg2::THREADS, AttnCfg2::SMEM_BYTES, s>>>(l->mapQ, l->mapKV, l->p);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 

@@ -134,10 +134,14 @@ struct RasterParams {
 };
 
 // One set-up sub-triangle, flattened to 32-bit words so a lane can broadcast it to its warp with shuffles.
+// The three edge functions are kept in coefficient form  E_i(cx, cy) = ea_i*cx + eb_i*cy + ec_i  (exact 64-bit integers, the
+// expansion of tri_eval's ((Xb-Xa)*(cy-Ya) - (Yb-Ya)*(cx-Xa))*sgn), so a pixel costs two multiplies per edge.
 struct RTri {
-  long long X[3], Y[3];
+  long long ea[3], eb[3], ec[3];
   float zw[3], iw[3], pad[3];
-  long long area;
+  float farea;                 // |area| as float (barycentric denominator)
+  int front;                   // area > 0
+  int tie;                     // bit i: an E_i == 0 pixel centre belongs to the triangle (top-left style rule)
   int px0, px1, py0, py1;
   uint32_t prim;
   int valid;
@@ -149,9 +153,20 @@ __device__ __forceinline__ void rtri_make(const WVtx* v, int S, uint32_t prim, R
   tri_setup(v, S, t);
   r.valid = 0;
   if (t.area == 0) return;
+  const long long sgn = t.area > 0 ? 1 : -1;
+  r.tie = 0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { r.X[i] = t.X[i]; r.Y[i] = t.Y[i]; r.zw[i] = t.zw[i]; r.iw[i] = t.iw[i]; r.pad[i] = v[i].pad; }
-  r.area = t.area;
+  for (int i = 0; i < 3; ++i) {
+    const int a = (i + 1) % 3, c = (i + 2) % 3;
+    const long long dx = (t.X[c] - t.X[a]) * sgn, dy = (t.Y[c] - t.Y[a]) * sgn;
+    r.ea[i] = -dy;
+    r.eb[i] = dx;
+    r.ec[i] = -(r.ea[i] * t.X[a] + r.eb[i] * t.Y[a]);
+    if ((dy > 0) || (dy == 0 && dx < 0)) r.tie |= 1 << i;
+    r.zw[i] = t.zw[i]; r.iw[i] = t.iw[i]; r.pad[i] = v[i].pad;
+  }
+  r.farea = static_cast<float>(sgn * t.area);
+  r.front = t.area > 0 ? 1 : 0;
   r.prim = prim;
   const long long minx = min(t.X[0], min(t.X[1], t.X[2])), maxx = max(t.X[0], max(t.X[1], t.X[2]));
   const long long miny = min(t.Y[0], min(t.Y[1], t.Y[2])), maxy = max(t.Y[0], max(t.Y[1], t.Y[2]));
@@ -166,16 +181,19 @@ __device__ __forceinline__ void rtri_make(const WVtx* v, int S, uint32_t prim, R
 }
 
 __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis, int simple) {
-  TriSetup t;
+  const long long cx = static_cast<long long>(px) * 256 + 128, cy = static_cast<long long>(py) * 256 + 128;
+  long long E[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { t.X[i] = r.X[i]; t.Y[i] = r.Y[i]; t.zw[i] = r.zw[i]; t.iw[i] = r.iw[i]; }
-  t.area = r.area;
-  float l0, l1, l2;
-  if (!tri_eval(t, px, py, l0, l1, l2)) return;
-  const float z = (l0 * t.zw[0] + l1 * t.zw[1]) + l2 * t.zw[2];
+  for (int i = 0; i < 3; ++i) {
+    const long long e = r.ea[i] * cx + r.eb[i] * cy + r.ec[i];
+    if (e < 0 || (e == 0 && !((r.tie >> i) & 1))) return;
+    E[i] = e;
+  }
+  const float l0 = static_cast<float>(E[0]) / r.farea, l1 = static_cast<float>(E[1]) / r.farea, l2 = static_cast<float>(E[2]) / r.farea;
+  const float z = (l0 * r.zw[0] + l1 * r.zw[1]) + l2 * r.zw[2];
   if (!(z > 0.f && z < 1.f)) return;
-  if (!simple && !(r.area > 0)) {
-    const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
+  if (!simple && !r.front) {
+    const float b0 = l0 * r.iw[0], b1 = l1 * r.iw[1], b2 = l2 * r.iw[2];
     const float bs = (b0 + b1) + b2;
     const float pad = ((b0 / bs) * r.pad[0] + (b1 / bs) * r.pad[1]) + (b2 / bs) * r.pad[2];
     if (pad > 0.001f) return;      // back-facing frustum padding is discarded (aggregation.fsh:23)
@@ -203,19 +221,10 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
     uint32_t* dst = reinterpret_cast<uint32_t*>(&b);
 #pragma unroll
     for (int i = 0; i < kRTriWords; ++i) dst[i] = __shfl_sync(0xffffffffu, src[i], leader);
-    // 8x8-pixel tiles of the bounding box; a tile is skipped when one edge function is negative at its most-inside
-    // corner (exact integer test, so the surviving pixels are decided by the same arithmetic as the small path)
-    const long long sgn = b.area > 0 ? 1 : -1;
-    long long ea[3], eb[3], ec[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int a = (i + 1) % 3, c = (i + 2) % 3;
-      ea[i] = -(b.Y[c] - b.Y[a]) * sgn;
-      eb[i] = (b.X[c] - b.X[a]) * sgn;
-      ec[i] = -(ea[i] * b.X[a] + eb[i] * b.Y[a]);
-    }
-    // The tiles of the bounding box are TESTED 32 at a time (one tile per lane; the frustum-ring slivers have bounding boxes
-    // of thousands of tiles of which a few dozen survive), the survivors are then scanned by the whole warp, 2 pixels per lane.
+    // 8x8-pixel tiles of the bounding box; a tile is skipped when one edge function is negative at its most-inside corner
+    // (exact integer test, so the surviving pixels are decided by the same arithmetic as the small path).  The tiles are
+    // TESTED 32 at a time (one tile per lane: the frustum-ring slivers have bounding boxes of thousands of tiles of which a
+    // few dozen survive); the survivors are then scanned by the whole warp, 2 pixels per lane.
     const int tx0 = b.px0 >> 3, tx1 = b.px1 >> 3, ty0 = b.py0 >> 3, ty1 = b.py1 >> 3;
     const int ntx = tx1 - tx0 + 1, nt = ntx * (ty1 - ty0 + 1);
     for (int base = 0; base < nt; base += 32) {
@@ -230,7 +239,7 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
         bool out = false;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const long long emax = ea[i] * (ea[i] > 0 ? cx1 : cx0) + eb[i] * (eb[i] > 0 ? cy1 : cy0) + ec[i];
+          const long long emax = b.ea[i] * (b.ea[i] > 0 ? cx1 : cx0) + b.eb[i] * (b.eb[i] > 0 ? cy1 : cy0) + b.ec[i];
           out = out || (emax < 0);
         }
         keep = !out;
@@ -251,7 +260,7 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
   }
 }
 
-__global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
+__global__ void __launch_bounds__(128, 4) raster_kernel(const RasterParams p) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int view = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31;
@@ -291,6 +300,8 @@ struct ResolveParams {
   float* depth;               // [B][S][S]
   float* mask_color;          // [B][S][S]  0/1
   float* mask_depth;          // [B][S][S]
+  float4* frag_c;             // [B][nviews][S*S] shaded fragment colour + weight of every source view (shade_kernel)
+  float* frag_d;              // [B][nviews][S*S] its window depth (1 where nothing was drawn)
 };
 
 __device__ __forceinline__ float shade_weight(const float* pos, const float* nrm, const float* cam, float edge, float pad, float ero) {
@@ -308,55 +319,73 @@ __device__ __forceinline__ float shade_weight(const float* pos, const float* nrm
   return fmaxf(w, 1e-16f);
 }
 
+// Pass 1 (one thread per (pixel, source view, sample): every covered fragment is shaded independently, so the dependent
+// gathers key -> face -> vertices -> texel of different views overlap instead of running one after the other per pixel):
+// fragment colour / weight and window depth exactly as aggregation.fsh produces them.
+__global__ void __launch_bounds__(128) shade_kernel(const ResolveParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y, b = blockIdx.z;
+  if (pix >= p.S * p.S) return;
+  const int px = pix % p.S, py = pix / p.S;       // framebuffer coordinates (row 0 = bottom)
+  const float* mvp = p.mvp + b * 16;
+  const size_t slot = (static_cast<size_t>(b) * p.nviews + i) * p.S * p.S + pix;
+  const unsigned long long key = p.vis[slot];
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  float depth = 1.0f;
+  if (key != ~0ull) {
+    depth = __uint_as_float(static_cast<uint32_t>(key >> 32));
+    const uint32_t prim = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+    const uint32_t f = prim >> 1, sub = prim & 1u;
+    const ViewRef vr = p.views[b * p.nviews + i];
+    WVtx in[3], poly[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[f * 3 + k], mvp, in[k]);
+    clip_near(in, poly);
+    WVtx tv[3];
+    tv[0] = poly[0];
+    tv[1] = sub ? poly[2] : poly[1];
+    tv[2] = sub ? poly[3] : poly[2];
+    TriSetup t;
+    tri_setup(tv, p.S, t);
+    float l0, l1, l2;
+    if (t.area > 0 && tri_eval(t, px, py, l0, l1, l2)) {     // front face: shade; back face keeps (0,0,0,0)
+      const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
+      const float bs = (b0 + b1) + b2;
+      const float c0 = b0 / bs, c1 = b1 / bs, c2 = b2 / bs;
+      float pos[3], nrm[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        pos[k] = (c0 * tv[0].pos[k] + c1 * tv[1].pos[k]) + c2 * tv[2].pos[k];
+        nrm[k] = (c0 * tv[0].nrm[k] + c1 * tv[1].nrm[k]) + c2 * tv[2].nrm[k];
+      }
+      const float uu = (c0 * tv[0].uv[0] + c1 * tv[1].uv[0]) + c2 * tv[2].uv[0];
+      const float vv = (c0 * tv[0].uv[1] + c1 * tv[1].uv[1]) + c2 * tv[2].uv[1];
+      const float edge = (c0 * tv[0].edge + c1 * tv[1].edge) + c2 * tv[2].edge;
+      const float pad = (c0 * tv[0].pad + c1 * tv[1].pad) + c2 * tv[2].pad;
+      const float ero = (c0 * tv[0].ero + c1 * tv[1].ero) + c2 * tv[2].ero;
+      int tx = static_cast<int>(floorf(uu * static_cast<float>(p.T))), ty = static_cast<int>(floorf(vv * static_cast<float>(p.T)));
+      tx = min(max(tx, 0), p.T - 1); ty = min(max(ty, 0), p.T - 1);
+      const float* tc = vr.tex + (static_cast<size_t>(ty) * p.T + tx) * 3;
+      c[0] = tc[0]; c[1] = tc[1]; c[2] = tc[2];
+      c[3] = shade_weight(pos, nrm, vr.cam, edge, pad, ero);
+    }
+  }
+  p.frag_c[slot] = make_float4(c[0], c[1], c[2], c[3]);
+  p.frag_d[slot] = depth;
+}
+
+// Pass 2 (one thread per pixel): aggregation.csh across the source views IN DRAW ORDER + read-back resolve.
 __global__ void __launch_bounds__(128) resolve_kernel(const ResolveParams p) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (pix >= p.S * p.S) return;
-  const int px = pix % p.S, py = pix / p.S;       // framebuffer coordinates (row 0 = bottom)
-  const float* mvp = p.mvp + b * 16;
+  const int px = pix % p.S, py = pix / p.S;
   float ac[4] = {0.f, 0.f, 0.f, 0.f}, ad[2] = {0.f, 0.f}, am[2] = {0.f, 0.f};
   for (int i = 0; i < p.nviews; ++i) {
-    const unsigned long long key = p.vis[(static_cast<size_t>(b) * p.nviews + i) * p.S * p.S + pix];
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    float depth = 1.0f;
-    if (key != ~0ull) {
-      depth = __uint_as_float(static_cast<uint32_t>(key >> 32));
-      const uint32_t prim = static_cast<uint32_t>(key & 0xFFFFFFFFull);
-      const uint32_t f = prim >> 1, sub = prim & 1u;
-      const ViewRef vr = p.views[b * p.nviews + i];
-      WVtx in[3], poly[4];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[f * 3 + k], mvp, in[k]);
-      clip_near(in, poly);
-      WVtx tv[3];
-      tv[0] = poly[0];
-      tv[1] = sub ? poly[2] : poly[1];
-      tv[2] = sub ? poly[3] : poly[2];
-      TriSetup t;
-      tri_setup(tv, p.S, t);
-      float l0, l1, l2;
-      if (t.area > 0 && tri_eval(t, px, py, l0, l1, l2)) {     // front face: shade; back face keeps (0,0,0,0)
-        const float b0 = l0 * t.iw[0], b1 = l1 * t.iw[1], b2 = l2 * t.iw[2];
-        const float bs = (b0 + b1) + b2;
-        const float c0 = b0 / bs, c1 = b1 / bs, c2 = b2 / bs;
-        float pos[3], nrm[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          pos[k] = (c0 * tv[0].pos[k] + c1 * tv[1].pos[k]) + c2 * tv[2].pos[k];
-          nrm[k] = (c0 * tv[0].nrm[k] + c1 * tv[1].nrm[k]) + c2 * tv[2].nrm[k];
-        }
-        const float uu = (c0 * tv[0].uv[0] + c1 * tv[1].uv[0]) + c2 * tv[2].uv[0];
-        const float vv = (c0 * tv[0].uv[1] + c1 * tv[1].uv[1]) + c2 * tv[2].uv[1];
-        const float edge = (c0 * tv[0].edge + c1 * tv[1].edge) + c2 * tv[2].edge;
-        const float pad = (c0 * tv[0].pad + c1 * tv[1].pad) + c2 * tv[2].pad;
-        const float ero = (c0 * tv[0].ero + c1 * tv[1].ero) + c2 * tv[2].ero;
-        int tx = static_cast<int>(floorf(uu * static_cast<float>(p.T))), ty = static_cast<int>(floorf(vv * static_cast<float>(p.T)));
-        tx = min(max(tx, 0), p.T - 1); ty = min(max(ty, 0), p.T - 1);
-        const float* tc = vr.tex + (static_cast<size_t>(ty) * p.T + tx) * 3;
-        c[0] = tc[0]; c[1] = tc[1]; c[2] = tc[2];
-        c[3] = shade_weight(pos, nrm, vr.cam, edge, pad, ero);
-      }
-    }
+    const size_t slot = (static_cast<size_t>(b) * p.nviews + i) * p.S * p.S + pix;
+    const float4 c4 = p.frag_c[slot];
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float depth = p.frag_d[slot];
     // aggregation.csh:18-43
     const float wc = c[3];
     const float wd = c[3] > 1e-14f ? 1.0f : (c[3] > 0.0f ? 1e-8f : 0.0f);
@@ -810,6 +839,8 @@ class Warp {
     IVID_CHECK_CUDA(cudaMalloc(&tex_, slots * n_ * n_ * 3 * 4));
     IVID_CHECK_CUDA(cudaMalloc(&views_dev_, slots * sizeof(ViewRef)));
     IVID_CHECK_CUDA(cudaMalloc(&vis_, slots * S_ * S_ * 8));
+    IVID_CHECK_CUDA(cudaMalloc(&frag_c_, slots * S_ * S_ * sizeof(float4)));
+    IVID_CHECK_CUDA(cudaMalloc(&frag_d_, slots * S_ * S_ * 4));
     IVID_CHECK_CUDA(cudaMalloc(&mvp_dev_, B_ * 16 * 4));
     IVID_CHECK_CUDA(cudaMalloc(&inv_dev_, B_ * 16 * 4));
     IVID_CHECK_CUDA(cudaMalloc(&pts_, static_cast<size_t>(B_) * V_ * 3 * 8));
@@ -831,7 +862,7 @@ class Warp {
   }
   ~Warp() {
     for (void* p : {static_cast<void*>(verts_), static_cast<void*>(faces_), static_cast<void*>(tex_), static_cast<void*>(views_dev_),
-                    static_cast<void*>(vis_), static_cast<void*>(mvp_dev_), static_cast<void*>(inv_dev_), static_cast<void*>(pts_),
+                    static_cast<void*>(vis_), static_cast<void*>(frag_c_), static_cast<void*>(frag_d_), static_cast<void*>(mvp_dev_), static_cast<void*>(inv_dev_), static_cast<void*>(pts_),
                     static_cast<void*>(nrm_), static_cast<void*>(dep_), static_cast<void*>(disc_), static_cast<void*>(raw_color_),
                     static_cast<void*>(raw_depth_), static_cast<void*>(raw_mc_), static_cast<void*>(raw_md_), static_cast<void*>(tmp8_),
                     static_cast<void*>(col8_), static_cast<void*>(dproj_), static_cast<void*>(m0_), static_cast<void*>(mr0_),
@@ -974,6 +1005,9 @@ class Warp {
     sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = nviews_; sp.S = S_; sp.T = n_;
     sp.nf_f = static_cast<float>(near_ * far_); sp.far_f = static_cast<float>(far_); sp.fn_f = static_cast<float>(far_ - near_);
     sp.color = raw_color_; sp.depth = raw_depth_; sp.mask_color = raw_mc_; sp.mask_depth = raw_md_;
+    sp.frag_c = frag_c_; sp.frag_d = frag_d_;
+    dim3 gsh((S_ * S_ + 127) / 128, nviews_, B_);
+    shade_kernel<<<gsh, 128, 0, st>>>(sp);
     dim3 gs((S_ * S_ + 127) / 128, B_);
     resolve_kernel<<<gs, 128, 0, st>>>(sp);
     IVID_CHECK_CUDA(cudaGetLastError());
@@ -1151,7 +1185,7 @@ class Warp {
   int V_ = 0, F_ = 0, nviews_ = 0, ksize_ = 0;
   bool views_dirty_ = true;
   float* verts_ = nullptr; uint32_t* faces_ = nullptr; float* tex_ = nullptr; ViewRef* views_dev_ = nullptr;
-  unsigned long long* vis_ = nullptr; float* mvp_dev_ = nullptr; float* inv_dev_ = nullptr;
+  unsigned long long* vis_ = nullptr; float4* frag_c_ = nullptr; float* frag_d_ = nullptr; float* mvp_dev_ = nullptr; float* inv_dev_ = nullptr;
   double* pts_ = nullptr; double* nrm_ = nullptr; float* dep_ = nullptr; int* disc_ = nullptr;
   float *raw_color_ = nullptr, *raw_depth_ = nullptr, *raw_mc_ = nullptr, *raw_md_ = nullptr;
   unsigned char *tmp8_ = nullptr, *col8_ = nullptr, *m0_ = nullptr, *mr0_ = nullptr;
