@@ -204,6 +204,12 @@ int ivid_warp_aggregate(ivid_warp_t* w, const float* target_mv_host, int shared_
 int ivid_warp_postfilter(ivid_warp_t* w, const float* color_dev, const float* depth_dev, const float* mask_color_dev,
                          const float* mask_depth_dev, const ivid_warp_params_t* params, float* cond_dev, void* stream);
 
+/* Free-view frame resolve (inference/render.py:74-84) of the LAST ivid_warp_render: colour = 8-bit LANCZOS down-sampling to
+ * image_size, depth = centre sample -> project_depth(project_near, project_far) -> 256-entry uint8 RGB colour table `lut_host`
+ * (cv2.COLORMAP_INFERNO pushed through colorize_depth's numpy steps).  Outputs uint8 [batch, H, W, 3] on the host. */
+int ivid_warp_resolve_frame(ivid_warp_t* w, double project_near, double project_far, const uint8_t* lut_host, uint8_t* color8_host,
+                            uint8_t* depth8_host, void* stream);
+
 /* Training-pair warp — replaces rgbd_3d.SimpleRenderer (moderngl_renderer.py:11-148, shaders/simple.{vsh,fsh}) and
  * rgbd_3d.utils.forward_backward_warp (utils.py:335-417; called per training item by datasets/base.py:215-266).
  * SimpleRenderer.render(mesh, color, modelview, fov) for a single-sample handle: the mesh is an image_size^2 (padding=None)

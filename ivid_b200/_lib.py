@@ -98,6 +98,7 @@ SIGNATURES = {
     "ivid_warp_get_mesh": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ivid_warp_render": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ivid_warp_aggregate": (c_int, [c_void_p, c_void_p, c_int, POINTER(WarpParamsT), c_void_p, c_void_p]),
+    "ivid_warp_resolve_frame": (c_int, [c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ivid_warp_render_simple": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ivid_warp_forward_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(WarpParamsT), c_void_p, c_void_p]),
     "ivid_warp_postfilter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(WarpParamsT), c_void_p, c_void_p]),

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
 // (4 registers each) until consumed, so a thread has 128 bytes of reads in flight although an item is only 16 bytes.
 // kHoist: the channel-group count divides the block size, so a thread keeps the same 8 channels on every trip and its 16
 // coefficients live in registers (saves 16 shared-memory loads per 16-byte item).
-template <bool kHoist>
+template <bool kHoist, bool kLo = false>
 __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParams p) {
   extern __shared__ float s_ab[];
   __shared__ float s_mean[64], s_rstd[64];
@@ -424,13 +424,13 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
       }
       if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
       pk[j] = pack_h2(y0, y1);
-      if (p.out_lo != nullptr) {
+      if (kLo) {
         const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&pk[j]));
         pl[j] = pack_h2(y0 - hi.x, y1 - hi.y);
       }
     }
     *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + (dst - p.out_act)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    if (kLo) *reinterpret_cast<uint4*>(p.out_lo + (dst - p.out_act)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   };
   if (kHoist) {
     // division-free addressing: the thread owns channel group cg and every (256 / c8)-th pixel starting at pr

@@ -323,7 +323,11 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   dim3 grid((pix_space + p.pix_per_block - 1) / p.pix_per_block, d.N);
   const size_t smem = static_cast<size_t>(C) * 8;
   if (p.mode == 0 && p.x0h != nullptr && p.out_raw16 == nullptr && p.out_raw32 == nullptr) {
-    if (256 % (C / 8) == 0) gn_apply_h16_kernel<true><<<grid, 256, smem, s>>>(p);
+    const bool hoist = 256 % (C / 8) == 0;
+    if (p.out_lo != nullptr) {        // output head only: also emits the low half of the two-term split
+      if (hoist) gn_apply_h16_kernel<true, true><<<grid, 256, smem, s>>>(p);
+      else gn_apply_h16_kernel<false, true><<<grid, 256, smem, s>>>(p);
+    } else if (hoist) gn_apply_h16_kernel<true><<<grid, 256, smem, s>>>(p);
     else gn_apply_h16_kernel<false><<<grid, 256, smem, s>>>(p);
   } else {
     gn_apply_kernel<<<grid, 256, smem, s>>>(p);

@@ -204,7 +204,9 @@ __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S,
 
 // Small triangles (the common 3x3-pixel case) are scanned by their own lane; triangles with a large bounding box (the
 // frustum ring and faces stretched across depth discontinuities) are broadcast to the warp and scanned by all 32 lanes.
-__device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane, int simple) {
+// `stash` = this warp's 32 rows of a shared-memory table: a lane parks its big triangle there and the warp reads the leader's row
+// (a broadcast load) instead of keeping two set-up triangles in registers and shuffling 36 words per triangle.
+__device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane, int simple, uint32_t (*stash)[kRTriWords]) {
   constexpr int kSmall = 48;
   const int w = r.valid ? (r.px1 - r.px0 + 1) : 0, h = r.valid ? (r.py1 - r.py0 + 1) : 0;
   const bool big = r.valid && (w * h > kSmall);
@@ -213,14 +215,20 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
       for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis, simple);
   }
   unsigned mask = __ballot_sync(0xffffffffu, big);
+  if (mask == 0u) return;
+  if (big) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < kRTriWords; ++i) stash[lane][i] = src[i];
+  }
+  __syncwarp();
   while (mask) {
     const int leader = __ffs(mask) - 1;
     mask &= mask - 1;
     RTri b;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&r);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&b);
 #pragma unroll
-    for (int i = 0; i < kRTriWords; ++i) dst[i] = __shfl_sync(0xffffffffu, src[i], leader);
+    for (int i = 0; i < kRTriWords; ++i) dst[i] = stash[leader][i];
     // 8x8-pixel tiles of the bounding box; a tile is skipped when one edge function is negative at its most-inside corner
     // (exact integer test, so the surviving pixels are decided by the same arithmetic as the small path).  The tiles are
     // TESTED 32 at a time (one tile per lane: the frustum-ring slivers have bounding boxes of thousands of tiles of which a
@@ -258,12 +266,15 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
       }
     }
   }
+  __syncwarp();      // the stash rows are reused by the next sub-triangle of this warp
 }
 
-__global__ void __launch_bounds__(128, 4) raster_kernel(const RasterParams p) {
+__global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int view = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31;
+  __shared__ uint32_t s_stash[128][kRTriWords];
+  uint32_t (*stash)[kRTriWords] = s_stash + (threadIdx.x & ~31);
   unsigned long long* vis = p.vis + (static_cast<size_t>(b) * p.nviews + view) * p.S * p.S;
   RTri t0, t1;
   t0.valid = 0; t1.valid = 0;
@@ -283,8 +294,8 @@ __global__ void __launch_bounds__(128, 4) raster_kernel(const RasterParams p) {
       rtri_make(q, p.S, static_cast<uint32_t>(fi) * 2u + 1u, t1);
     }
   }
-  rtri_raster(t0, p.S, vis, lane, p.simple);
-  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane, p.simple);
+  rtri_raster(t0, p.S, vis, lane, p.simple, stash);
+  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane, p.simple, stash);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -767,6 +778,27 @@ __global__ void post_edge_kernel(const PostParams p) {
   // written to a second plane to keep the stencil race-free: reuse the upper bits
   m[idx] = (m[idx] & 1) | (((m[idx] & 1) && hits < 3) ? 2 : 0);
 }
+// Free-view frames (inference/render.py:74-84): centre point sample of the linear depth -> project_depth -> colour map.
+// idx = uint8((clip(1 - d, 0, 1) * 255)) in float32 exactly as numpy evaluates colorize_depth(d, min=0, max=1) on a float32
+// array; `lut` is the 256-entry uint8 RGB table the host derived from cv2.COLORMAP_INFERNO through the same numpy steps.
+__global__ void depth_colormap_kernel(const float* __restrict__ depth, int S, int n, int ssaa, float near_f, float far_f,
+                                      float inv_near_f, float denom_f, const unsigned char* __restrict__ lut,
+                                      unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= n * n) return;
+  const int y = idx / n, x = idx % n;
+  const int off = ssaa / 2;
+  float d = depth[static_cast<size_t>(b) * S * S + static_cast<size_t>(y * ssaa + off) * S + (x * ssaa + off)];
+  d = fminf(fmaxf(d, near_f), far_f);
+  d = (inv_near_f - 1.0f / d) / denom_f;
+  float v = 1.0f - d;
+  v = fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f;
+  const int k = static_cast<int>(v);
+  unsigned char* o = out + (static_cast<size_t>(b) * n * n + idx) * 3;
+  o[0] = lut[k * 3 + 0]; o[1] = lut[k * 3 + 1]; o[2] = lut[k * 3 + 2];
+}
+
 // erosion of mask for mask_rgb, final products (utils.py:464-469)
 __global__ void post_final_kernel(const PostParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -866,7 +898,7 @@ class Warp {
                     static_cast<void*>(nrm_), static_cast<void*>(dep_), static_cast<void*>(disc_), static_cast<void*>(raw_color_),
                     static_cast<void*>(raw_depth_), static_cast<void*>(raw_mc_), static_cast<void*>(raw_md_), static_cast<void*>(tmp8_),
                     static_cast<void*>(col8_), static_cast<void*>(dproj_), static_cast<void*>(m0_), static_cast<void*>(mr0_),
-                    static_cast<void*>(coef_dev_), static_cast<void*>(bounds_dev_)})
+                    static_cast<void*>(coef_dev_), static_cast<void*>(bounds_dev_), static_cast<void*>(lut_dev_)})
       if (p) cudaFree(p);
   }
   int image_size() const { return n_; }
@@ -1091,6 +1123,28 @@ class Warp {
     nviews_ = 0;
   }
 
+  // inference/render.py:74-84 on the last raw render: 8-bit LANCZOS colour + colour-mapped projected depth, both uint8
+  // [B][n][n][3] on the host (two 48 KB copies per frame instead of the 640^2 float images)
+  void resolve_frame(double pnear, double pfar, const unsigned char* lut_host, unsigned char* color8_host, unsigned char* depth8_host,
+                     cudaStream_t st) {
+    IVID_CHECK_CUDA(cudaSetDevice(device_));
+    ivid_warp_params_t wp{};
+    wp.near = pnear; wp.far = pfar; wp.erode_rgb = 1;
+    PostParams pp = post_params(raw_color_, raw_depth_, raw_mc_, raw_md_, wp, nullptr);
+    dim3 gh((S_ * n_ + 127) / 128, B_), gn((n_ * n_ + 127) / 128, B_);
+    lanczos_h_kernel<<<gh, 128, 0, st>>>(pp);
+    lanczos_v_kernel<<<gn, 128, 0, st>>>(pp);
+    if (lut_dev_ == nullptr) IVID_CHECK_CUDA(cudaMalloc(&lut_dev_, 768));
+    IVID_CHECK_CUDA(cudaMemcpyAsync(lut_dev_, lut_host, 768, cudaMemcpyHostToDevice, st));
+    unsigned char* d8 = tmp8_;      // the horizontal-pass scratch is free again after the vertical pass
+    depth_colormap_kernel<<<gn, 128, 0, st>>>(raw_depth_, S_, n_, S_ / n_, pp.near_f, pp.far_f, pp.inv_near_f, pp.denom_f, lut_dev_, d8);
+    IVID_CHECK_CUDA(cudaGetLastError());
+    const size_t bytes = static_cast<size_t>(B_) * n_ * n_ * 3;
+    IVID_CHECK_CUDA(cudaMemcpyAsync(color8_host, col8_, bytes, cudaMemcpyDeviceToHost, st));
+    IVID_CHECK_CUDA(cudaMemcpyAsync(depth8_host, d8, bytes, cudaMemcpyDeviceToHost, st));
+    IVID_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+
   void copy_raw(float* color, float* depth, float* mc, float* md, cudaStream_t st) {
     const size_t px = static_cast<size_t>(B_) * S_ * S_;
     if (color) IVID_CHECK_CUDA(cudaMemcpyAsync(color, raw_color_, px * 12, cudaMemcpyDeviceToDevice, st));
@@ -1191,6 +1245,7 @@ class Warp {
   unsigned char *tmp8_ = nullptr, *col8_ = nullptr, *m0_ = nullptr, *mr0_ = nullptr;
   float* dproj_ = nullptr;
   int *coef_dev_ = nullptr, *bounds_dev_ = nullptr;
+  unsigned char* lut_dev_ = nullptr;
   std::vector<float> cams_;
 };
 
@@ -1261,6 +1316,13 @@ int ivid_warp_aggregate(ivid_warp_t* w, const float* target_mv_host, int shared_
   return warp_guard([&] {
     IVID_REQUIRE(w && target_mv_host && params && cond_dev, "aggregate: NULL argument");
     w->impl->aggregate(target_mv_host, shared_modelview != 0, *params, cond_dev, static_cast<cudaStream_t>(stream));
+  });
+}
+int ivid_warp_resolve_frame(ivid_warp_t* w, double project_near, double project_far, const uint8_t* lut_host, uint8_t* color8_host,
+                            uint8_t* depth8_host, void* stream) {
+  return warp_guard([&] {
+    IVID_REQUIRE(w && lut_host && color8_host && depth8_host, "resolve_frame: NULL argument");
+    w->impl->resolve_frame(project_near, project_far, lut_host, color8_host, depth8_host, static_cast<cudaStream_t>(stream));
   });
 }
 int ivid_warp_render_simple(ivid_warp_t* w, const float* verts_host, int nverts, const uint32_t* faces_host, int nfaces,

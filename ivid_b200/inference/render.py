@@ -57,9 +57,27 @@ def resolve_frame(frame, image_size=128):
     return col, dep
 
 
-def render_scene(renderer, scene_path, modelviews, atol=0.03, rtol=0.03, erode_rgb=3):
-    """-> (colors uint8 [F,n,n,3], depths uint8 [F,n,n,3]) for the F target views."""
+_LUT = None
+
+
+def depth_colour_table():
+    """uint8 [256,3]: what `(colorize_depth(d, min=0, max=1) * 255).astype(np.uint8)` yields for each of the 256 quantised
+    depths (cv2.COLORMAP_INFERNO -> RGB -> /255 -> *255 -> truncation, the reference's round trip render.py:80-82)."""
+    global _LUT
+    if _LUT is None:
+        import cv2
+        rgb = cv2.cvtColor(cv2.applyColorMap(np.arange(256, dtype=np.uint8)[None], cv2.COLORMAP_INFERNO), cv2.COLOR_BGR2RGB)[0]
+        _LUT = ((rgb / 255 * (1 - 0) + 0) * 255).astype(np.uint8)
+    return _LUT
+
+
+def render_scene(renderer, scene_path, modelviews, atol=0.03, rtol=0.03, erode_rgb=3, resolve_on_device=True):
+    """-> (colors uint8 [F,n,n,3], depths uint8 [F,n,n,3]) for the F target views.  The SSAA resolve (8-bit LANCZOS) and the
+    depth colour map run on the device (AggregationRenderer.render_resolved); resolve_on_device=False keeps the reference's
+    numpy / PIL / cv2 steps on the host (`resolve_frame`), bit-identical by construction."""
     meshes, colors = load_scene(scene_path, atol=atol, rtol=rtol, erode_rgb=erode_rgb)
+    if resolve_on_device:
+        return renderer.render_resolved(meshes, colors, list(modelviews), lut=depth_colour_table())
     res = renderer.render(meshes, colors, list(modelviews))
     frames = res if isinstance(res, list) else [res]
     cols, deps = zip(*(resolve_frame(f, renderer.image_size) for f in frames))

@@ -104,6 +104,33 @@ class AggregationRenderer(_Native):
             }))
         return ret if len(ret) > 1 else ret[0]
 
+    def render_resolved(self, meshes, colors, modelviews, fov=45.0, project_near=0.5, project_far=100, lut=None):
+        """Free-view frames resolved on the device (inference/render.py:74-84): for every target modelview the aggregated
+        render at render_size is down-sampled by the 8-bit LANCZOS kernels and its centre-sampled, projected depth is colour
+        mapped through `lut` (uint8 [256,3]); only the two uint8 [image_size, image_size, 3] images cross PCIe.
+        Returns (colors uint8 [F,n,n,3], depths uint8 [F,n,n,3])."""
+        L = _lib.lib()
+        _lib.check(L.ivid_warp_reset(self._handle))
+        for i, mesh in enumerate(meshes):
+            v = mesh.vertices if hasattr(mesh, "vertices") else mesh["vertices"]
+            vb = np.ascontiguousarray(np.concatenate([v["position"], v["normal"], v["uv"], v["flag"]], axis=-1).astype(np.float32))
+            faces = np.ascontiguousarray((mesh.faces if hasattr(mesh, "faces") else mesh["faces"]).astype(np.uint32))
+            col = np.ascontiguousarray(colors[i].astype(np.float32))
+            mv = _mv(mesh.modelview if hasattr(mesh, "modelview") else mesh["modelview"])
+            _lib.check(L.ivid_warp_set_mesh(self._handle, 0, i, vb.ctypes.data, faces.ctypes.data, col.ctypes.data, mv.ctypes.data))
+        n = self.image_size
+        lut = np.ascontiguousarray(lut, dtype=np.uint8).reshape(256, 3)
+        cols, deps = [], []
+        with torch.cuda.device(torch.device("cuda", self.device)):
+            for t in (modelviews if isinstance(modelviews, list) else [modelviews]):
+                tm = _mv(t)
+                _lib.check(L.ivid_warp_render(self._handle, tm.ctypes.data, 1, float(fov), None, None, None, None, self._stream()))
+                c8 = np.empty((n, n, 3), np.uint8); d8 = np.empty((n, n, 3), np.uint8)
+                _lib.check(L.ivid_warp_resolve_frame(self._handle, float(project_near), float(project_far), lut.ctypes.data, c8.ctypes.data,
+                                                     d8.ctypes.data, self._stream()))
+                cols.append(c8); deps.append(d8)
+        return np.stack(cols, axis=0), np.stack(deps, axis=0)
+
     def _set_views(self, n):
         cur = ctypes.c_int()
         _lib.check(_lib.lib().ivid_warp_num_views(self._handle, ctypes.byref(cur)))

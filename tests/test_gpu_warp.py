@@ -224,6 +224,13 @@ def test_free_view_render_matches_oracle(wg, tmp_path):
         print(f"[parity] free-view frame {j}: resolved colour pixels off by more than one 8-bit step: {off:.2e}")
         assert off < 1e-3
         assert (d8 != d8r).mean() < 1e-2
+    # the device-side resolve (8-bit LANCZOS kernels + depth colour table) is bit-identical to the host numpy / PIL / cv2 steps
+    from ivid_b200.inference.render import depth_colour_table
+    cd, dd = gpu_r.render_resolved(meshes, cols, targets, lut=depth_colour_table())
+    for j in range(2):
+        c8, d8 = resolve_frame(got[j], 128)
+        assert np.array_equal(cd[j], c8), "device LANCZOS resolve differs from PIL"
+        assert np.array_equal(dd[j], d8), "device depth colour map differs from colorize_depth"
 
 
 def test_unpadded_mesh_and_simple_renderer_match_oracle(wg):

@@ -38,6 +38,12 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 res = r.render(meshes, cols, traj)
 torch.cuda.synchronize(); t_render = time.perf_counter() - t0
 t0 = time.perf_counter(); out = [resolve_frame(f, 128) for f in res]; t_resolve = time.perf_counter() - t0
+from ivid_b200.inference.render import depth_colour_table
+r.render_resolved(meshes, cols, traj[:2], lut=depth_colour_table())
+torch.cuda.synchronize(); t0 = time.perf_counter()
+cd, dd = r.render_resolved(meshes, cols, traj, lut=depth_colour_table())
+torch.cuda.synchronize(); t_dev = time.perf_counter() - t0
+same = bool(np.array_equal(cd[1], out[1][0]) and np.array_equal(dd[1], out[1][1]))
 # CPU oracle leg: same scene, 2 frames
 stored = load_scene_views(path)
 t0 = time.perf_counter()
@@ -52,5 +58,7 @@ agree = float((ref.mask_color == res[1]["mask_color"]).mean())
 print(json.dumps({"workload": f"free-view rendering, 27 source views, {frames}-frame swing, 640x640 (5x SSAA) -> 128x128",
                   "load_scene_remesh_ms": t_load * 1e3, "render_ms_per_frame": t_render / frames * 1e3,
                   "resolve_ms_per_frame_host": t_resolve / frames * 1e3, "frames_per_s_render": frames / t_render,
+                  "render_plus_device_resolve_ms_per_frame": t_dev / frames * 1e3, "frames_per_s_resolved_on_device": frames / t_dev,
+                  "device_resolve_equals_host": same,
                   "cpu_oracle": {"remesh_ms": t_mesh_cpu * 1e3, "render_ms_per_frame": t_cpu * 1e3, "cores": 1, "kind": "port"},
                   "mask_agreement_frame1": agree, "coverage": float(res[1]["mask_color"].mean())}))
