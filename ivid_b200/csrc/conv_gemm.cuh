@@ -44,6 +44,7 @@ struct ConvGemmParams {
   int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
+  int mc_n, mc_m;              // cluster-multicast mode (kMc): cluster = mc_m pixel tiles x mc_n column blocks
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
 
@@ -57,6 +58,8 @@ struct ConvMaps {
   CUtensorMap bh;              // packed weights, half-width box (split tail items)
   CUtensorMap out, res;        // epilogue: output tile store, residual tile load
   CUtensorMap out16;           // optional fp16 copy of an fp32 output ([32 px][64 ch] boxes)
+  CUtensorMap a_mc[3];         // kMc: activation slice (128 / mc_n pixels) of each segment
+  CUtensorMap b_mc;            // kMc: weight slice (BN / mc_m rows)
 };
 
 template <int BN, int kCtas = 1>
@@ -79,12 +82,27 @@ struct ConvGemmCfg {
   static constexpr int THREADS = 256;
 };
 
-template <int BN, int kCtas = 1>
+// kMc (cluster multicast, low-resolution levels): a cluster of mc_m x mc_n CTAs computes mc_m pixel tiles x mc_n column blocks.
+// The mc_n CTAs of a row need the SAME activation tile and the mc_m CTAs of a column the SAME weight tile, so every CTA loads
+// only a 1/mc_n slice of its activation tile and a 1/mc_m slice of its weight tile and multicasts them to its row / column:
+// the L2 -> shared-memory traffic per CTA and k-block drops from 32 KB to 16/mc_n + 16/mc_m KB (12 KB for 2 x 4), which is what
+// bounds the 8x8 level (M = 2048 pixels: every CTA used to stream its own operands, 9 TB/s of L2 reads at 590 TFLOP/s).
+// A stage may be refilled once every CTA that RECEIVES this CTA's slices has consumed it: the MMA commits arrive (multicast) on
+// the empty barriers of the whole row and column, which therefore count mc_n + mc_m - 1 arrivals.
+template <int BN, int kCtas = 1, bool kMc = false>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, kCtas>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!kMc || kCtas == 1, "multicast mode uses single-CTA MMAs");
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int mc_rank = kMc ? static_cast<int>(cluster_ctarank()) : 0;
+  const int mc_rn = kMc ? mc_rank % p.mc_n : 0, mc_rm = kMc ? mc_rank / p.mc_n : 0;
+  uint16_t row_mask = 0, col_mask = 0;
+  if constexpr (kMc) {
+    row_mask = static_cast<uint16_t>(((1u << p.mc_n) - 1u) << (mc_rm * p.mc_n));
+    for (int i = 0; i < p.mc_m; ++i) col_mask |= static_cast<uint16_t>(1u << (i * p.mc_n + mc_rn));
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;            // 1024-aligned (TMA 128B swizzle)
@@ -107,7 +125,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kMc ? static_cast<uint32_t>(p.mc_n + p.mc_m - 1) : 1u);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -121,16 +139,26 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
-  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();      // peer barriers initialised before any remote signal
+  if constexpr (kCtas == 2 || kMc) cluster_sync_all(); else __syncthreads();      // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work items of this CTA: tiles (kCtas == 1) or tile PAIRS of its cluster (kCtas == 2; CTA `rank` owns m-tile 2*pair+rank)
-  const int w_first = (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int w_stride = (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // work items of this CTA: tiles (kCtas == 1), tile PAIRS of its cluster (kCtas == 2; CTA `rank` owns m-tile 2*pair+rank) or
+  // cluster tiles (kMc: mc_m pixel tiles x mc_n column blocks; every CTA of a cluster walks the same item sequence)
+  const int mc_size = kMc ? p.mc_n * p.mc_m : 1;
+  const int w_first = kMc ? static_cast<int>(blockIdx.x) / mc_size : (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int w_stride = kMc ? static_cast<int>(gridDim.x) / mc_size : (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int w_limit = p.num_items;
   // work item -> (pixel-tile index of the CTA (pair), first output column, width)
   auto decode = [&](int w, int& mtp, int& colbase, int& ncols) {
+    if constexpr (kMc) {
+      const int ncb = p.n_blocks / p.mc_n;
+      const int mt_c = w / ncb, nb_c = w - mt_c * ncb;
+      mtp = mt_c * p.mc_m + mc_rm;
+      colbase = (nb_c * p.mc_n + mc_rn) * BN;
+      ncols = BN;
+      return;
+    }
     int f = w, half = 0;
     ncols = BN;
     if (w >= p.full_items) {
@@ -180,7 +208,16 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
-            if constexpr (kCtas == 2) {
+            if constexpr (kMc) {
+              // own barrier expects the whole tile; the bytes arrive as slices multicast by the CTAs of this row / column
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+              const int srows = 128 / p.mc_n;                       // pixels of one activation slice (multiple of 8)
+              const int r0 = mc_rn * srows;
+              const int dn = r0 / (p.TW * p.TH), dh = (r0 / p.TW) % p.TH;
+              tma_load_4d_mc(&maps.a_mc[seg], &full_bar[stage], sa + r0 * 128, ch * 64, w0 + dx, h0 + dy + dh, n0 + dn, row_mask);
+              const int brows = BN / p.mc_m;
+              tma_load_2d_mc(&maps.b_mc, &full_bar[stage], sb + mc_rm * brows * 128, kcol, colbase + mc_rm * brows, col_mask);
+            } else if constexpr (kCtas == 2) {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + b_bytes));
               const uint32_t bar = full0 + stage * 8;
               tma_load_4d_2sm(mapA, bar, sa, ch * 64, w0 + dx, h0 + dy, n0);
@@ -223,8 +260,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           if constexpr (kCtas == 2) mma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           else mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        // frees the smem slot (in both CTAs) once the MMAs above have consumed it
-        if constexpr (kCtas == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+        // frees the smem slot (in both CTAs / in every CTA that multicasts into it) once the MMAs above have consumed it
+        if constexpr (kMc) tc_commit_mc(&empty_bar[stage], static_cast<uint16_t>(row_mask | col_mask));
+        else if constexpr (kCtas == 2) tc_commit_2sm(&empty_bar[stage]);
+        else tc_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // accumulator complete -> epilogue (of both CTAs)
@@ -631,7 +670,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   }
 
   tc_fence_before();
-  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();      // the peer's smem / TMEM stay alive until both are done
+  if constexpr (kCtas == 2 || kMc) cluster_sync_all(); else __syncthreads();      // the peers' smem / TMEM stay alive until all are done
   if (warp == 2) {
     tc_fence_after();
     if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);

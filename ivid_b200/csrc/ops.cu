@@ -21,6 +21,7 @@ struct ConvLaunch {
   int BN;
   int grid;
   int ctas = 1;          // 2 = CTA-pair kernel (cluster of 2, cta_group::2 MMA)
+  int mc = 0;            // > 0: cluster-multicast kernel, cluster size mc = mc_n * mc_m
 };
 
 int conv_pad_cout(int cout) {
@@ -69,6 +70,29 @@ bool conv_can_out16(int cout) {
   static const int dbg = [] { const char* e = getenv("IVID_CONV_DEBUG"); return e ? atoi(e) : 0; }();
   static const bool off = getenv("IVID_NO_OUT16") != nullptr;
   return cout % 64 == 0 && !(dbg & 16) && !off;
+}
+
+// how many clusters of `csize` multicast-conv CTAs the device can hold at once (one CTA per SM, clusters stay inside a GPC)
+static int max_mc_clusters(int csize) {
+  static int cache[17] = {0};
+  if (cache[csize] == 0) {
+    using Cfg = ConvGemmCfg<128, 1>;
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(csize * (sm_count() / csize));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<128, 1, true>, &cfg);
+    if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = std::max(1, (sm_count() / csize) * 3 / 4); }
+    cache[csize] = n;
+  }
+  return cache[csize];
 }
 
 ConvLaunch* conv_launch_create(const ConvDesc& d) {
@@ -140,6 +164,36 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
       }
     }
   }
+  // Cluster multicast on the low-resolution levels (single-CTA N = 128 tiles, few pixel tiles): see conv_gemm_kernel<.., kMc>.
+  p.mc_n = 1; p.mc_m = 1;
+  {
+    static const bool mc_ok = getenv("IVID_NO_MC") == nullptr;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    if (mc_ok && l->ctas == 1 && l->BN == 128 && d.H <= 16 && m_tiles >= 2) {
+      const int cn = p.n_blocks % 4 == 0 ? 4 : (p.n_blocks % 2 == 0 ? 2 : 1);
+      const int cm = m_tiles % 2 == 0 ? 2 : 1;
+      if (cn * cm >= 2) {
+        p.mc_n = cn; p.mc_m = cm;
+        l->mc = cn * cm;
+        const int srows = 128 / cn;
+        const int bh = srows >= p.TW * p.TH ? p.TH : srows / p.TW, bn = srows >= p.TW * p.TH ? srows / (p.TW * p.TH) : 1;
+        IVID_REQUIRE(bh >= 1 && srows % 8 == 0, "conv: multicast slice geometry");
+        auto slice_map = [&](const void* base, int C) {
+          const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.N)};
+          const uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(d.W) * C * 2, static_cast<uint64_t>(d.H) * d.W * C * 2};
+          const uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+          return make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        };
+        M.a_mc[0] = slice_map(d.act0, d.C0);
+        M.a_mc[1] = d.C1 > 0 ? slice_map(d.act1, d.C1) : M.a_mc[0];
+        M.a_mc[2] = d.C2 > 0 ? slice_map(d.act2, d.C2) : M.a_mc[0];
+        M.b_mc = make_weight_map(d.weight, d.cout_pad, Ktot, l->BN / cm);
+        p.num_items = (m_tiles / cm) * (p.n_blocks / cn);
+        p.full_items = p.num_items;
+      }
+    }
+  }
+  if (l->mc == 0) { M.a_mc[0] = M.a[0]; M.a_mc[1] = M.a[0]; M.a_mc[2] = M.a[0]; M.b_mc = M.b; }
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
   M.out = M.a[0]; M.res = M.a[0]; M.out16 = M.a[0];
   p.out16 = 0;
@@ -185,6 +239,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   // fused statistics are produced by the TMA epilogues only
   if (p.stats != nullptr && p.epi_tma == 0) throw Error(kErrInvalidArgument, "conv: fused statistics need a TMA epilogue (Cout % 64 == 0)");
   l->grid = l->ctas == 2 ? 2 * std::min(p.num_items, sm_count() / 2) : std::min(p.num_items, sm_count());
+  if (l->mc > 0) l->grid = l->mc * std::min(p.num_items, max_mc_clusters(l->mc));
   return l;
 }
 void conv_launch_destroy(ConvLaunch* l) { delete l; }
@@ -214,12 +269,27 @@ static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
   cfg.numAttrs = 1;
   IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->maps, l->p));
 }
+static void run_conv_mc(const ConvLaunch* l, cudaStream_t s) {
+  using Cfg = ConvGemmCfg<128, 1>;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(l->grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = l->mc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<128, 1, true>, l->maps, l->p));
+}
 void conv_launch_run_out(const ConvLaunch* l, void* out, cudaStream_t s) {
   ConvLaunch tmp = *l;
   tmp.p.out = out;
   conv_launch_run(&tmp, s);
 }
 void conv_launch_run(const ConvLaunch* l, cudaStream_t s) {
+  if (l->mc > 0) { run_conv_mc(l, s); return; }
   if (l->ctas == 2) { run_conv_pair(l, s); return; }
   switch (l->BN) {
     case 256: run_conv<256>(l, s); break;

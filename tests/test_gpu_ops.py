@@ -33,6 +33,12 @@ CONV_CASES = [
     (2, 64, 64, 64, 16, 3),      # narrow Cout (BN=16 path, output head shape)
     (1, 128, 128, 256, 256, 3),  # the dominant shape of the large model
     (2, 64, 64, 64, 768, 3),     # 96 tile pairs on 74 SM pairs: the last round runs as half-width items
+    # cluster-multicast kernel (low-resolution levels, N = 128 tiles): clusters of mc_m pixel tiles x mc_n column blocks
+    (4, 8, 8, 256, 512, 3),      # 2 x 4 cluster (8 CTAs): activation slices of 32 pixels, weight slices of 64 rows
+    (8, 8, 8, 128, 256, 3),      # 2 x 2 cluster, 2 cluster items per cluster row
+    (32, 8, 8, 1024, 1024, 3),   # the 8x8 level of the large model at the benchmark batch: 16 clusters of 8
+    (6, 16, 16, 128, 384, 1),    # 16x16 tiles (slices along rows), 3 column blocks: 2 x 1 cluster
+    (4, 16, 16, 64, 640, 3),     # 5 column blocks (odd): 2 x 1 cluster, weight multicast only
 ]
 
 
@@ -70,6 +76,24 @@ def test_conv_skip_segment_residual_and_fp16_out():
     assert G.report("conv3x3 + identity residual", out2.permute(0, 3, 1, 2), ref2) < 2e-5
     out3 = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3, out_fp16=True)
     assert G.report("conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), F.conv2d(a.half().float(), w.half().float(), b, padding=1)) < 5e-4
+
+
+def test_conv_multicast_residual_stats_paths():
+    """Cluster-multicast kernel through the residual-prefetch epilogue, the fp16-output epilogue and the 1x1 skip segment."""
+    rng = _rng(21)
+    N, H, W, C, Cx = 8, 8, 8, 512, 256
+    a = _t(rng, N, C, H, W); x = _t(rng, N, Cx, H, W); res = _t(rng, N, C, H, W)
+    w = _t(rng, C, C, 3, 3, scale=1 / math.sqrt(9 * C)); b = _t(rng, C, scale=0.1)
+    ws = _t(rng, C, Cx, 1, 1, scale=1 / math.sqrt(Cx)); bs = _t(rng, C, scale=0.1)
+    base = F.conv2d(a.half().float(), w.half().float(), b, padding=1)
+    an = a.half().permute(0, 2, 3, 1).contiguous().cuda()
+    out = G.conv2d(an, w, b, 3, residual=res.permute(0, 2, 3, 1).contiguous().cuda())
+    assert G.report("multicast: conv3x3 + residual", out.permute(0, 3, 1, 2), base + res) < 2e-5
+    out16 = G.conv2d(an, w, b, 3, out_fp16=True)
+    assert G.report("multicast: conv3x3 fp16 out", out16.float().permute(0, 3, 1, 2), base) < 5e-4
+    outs = G.conv2d(an, w, b, 3, act2=x.half().permute(0, 2, 3, 1).contiguous().cuda(), w2=ws, b2=bs)
+    assert G.report("multicast: conv3x3 + 1x1 skip segment", outs.permute(0, 3, 1, 2),
+                    base + F.conv2d(x.half().float(), ws.half().float(), bs)) < 2e-5
 
 
 def test_conv_split_tail_residual_and_fp16_out():
