@@ -40,7 +40,8 @@ int conv_pick_bn(int cout_pad, int m_tiles) {
       const int sms = sm_count();
       const long t256 = static_cast<long>(m_tiles) * (cout_pad / 256), t128 = static_cast<long>(m_tiles) * (cout_pad / 128);
       const double cost256 = static_cast<double>((t256 + sms - 1) / sms) * 1.0;
-      const double cost128 = static_cast<double>((t128 + sms - 1) / sms) * 0.72;   // half the work per tile at ~70% of the N=256 efficiency (smem-operand bound)
+      static const double f128 = getenv("IVID_BN128_COST") ? atof(getenv("IVID_BN128_COST")) : 0.72;
+      const double cost128 = static_cast<double>((t128 + sms - 1) / sms) * f128;   // half the work per tile at ~70% of the N=256 efficiency (smem-operand bound)
       if (cost128 < cost256) return 128;
     }
     return 256;
@@ -167,7 +168,10 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   // Cluster multicast on the low-resolution levels (single-CTA N = 128 tiles, few pixel tiles): see conv_gemm_kernel<.., kMc>.
   p.mc_n = 1; p.mc_m = 1;
   {
-    static const bool mc_ok = getenv("IVID_NO_MC") == nullptr;
+    // Measured on B200 (profiles/per_op_r02e_*.json): 1.3x (2 x 2 clusters) to 2.4x (2 x 4) SLOWER than independent CTAs - the
+    // lock-step of 4-8 CTAs per stage and the small multicast boxes cost more than the 2.7x lower L2 traffic saves.  Kept as an
+    // opt-in experiment (IVID_MC=1, read at plan-build time), exercised by tests/test_gpu_ops.py.
+    const bool mc_ok = getenv("IVID_MC") != nullptr && getenv("IVID_MC")[0] == '1';
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     if (mc_ok && l->ctas == 1 && l->BN == 128 && d.H <= 16 && m_tiles >= 2) {
       const int cn = p.n_blocks % 4 == 0 ? 4 : (p.n_blocks % 2 == 0 ? 2 : 1);
@@ -365,7 +369,8 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.x0 = static_cast<const float*>(d.x0); p.x1 = static_cast<const float*>(d.x1); p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
   p.x0h = d.x0_half ? reinterpret_cast<const __half*>(d.x0) : nullptr;
   p.x1h = d.x0_half ? reinterpret_cast<const __half*>(d.x1) : nullptr;
-  p.silu = d.silu;
+  static const bool silu_sfu = getenv("IVID_SILU_SFU") != nullptr;      // previous SiLU (ex2 + rcp on the SFU) for same-box A/B
+  p.silu = d.silu ? (silu_sfu ? 2 : 1) : 0;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);

@@ -42,8 +42,21 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture(params=["default", "multicast"])
+def conv_mode(request, monkeypatch):
+    """Every conv case runs through the default kernels and through the opt-in cluster-multicast kernel (IVID_MC=1 is read when
+    a launch is created; it only takes effect on low-resolution N = 128 layers)."""
+    if request.param == "multicast":
+        monkeypatch.setenv("IVID_MC", "1")
+    else:
+        monkeypatch.delenv("IVID_MC", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k", CONV_CASES)
-def test_conv_matches_torch(N, H, W, Cin, Cout, k):
+def test_conv_matches_torch(N, H, W, Cin, Cout, k, conv_mode):
+    if conv_mode == "multicast" and H > 16:
+        pytest.skip("multicast mode only changes low-resolution layers")
     rng = _rng(hash((N, H, W, Cin, Cout, k)) % 2**31)
     x = _t(rng, N, Cin, H, W)
     w = _t(rng, Cout, Cin, k, k, scale=1 / math.sqrt(Cin * k * k))
@@ -78,8 +91,9 @@ def test_conv_skip_segment_residual_and_fp16_out():
     assert G.report("conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), F.conv2d(a.half().float(), w.half().float(), b, padding=1)) < 5e-4
 
 
-def test_conv_multicast_residual_stats_paths():
+def test_conv_multicast_residual_stats_paths(monkeypatch):
     """Cluster-multicast kernel through the residual-prefetch epilogue, the fp16-output epilogue and the 1x1 skip segment."""
+    monkeypatch.setenv("IVID_MC", "1")
     rng = _rng(21)
     N, H, W, C, Cx = 8, 8, 8, 512, 256
     a = _t(rng, N, C, H, W); x = _t(rng, N, Cx, H, W); res = _t(rng, N, C, H, W)
