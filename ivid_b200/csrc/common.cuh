@@ -31,18 +31,6 @@ __device__ __forceinline__ bool elect_one_sync() {
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-// SiLU for the GroupNorm-apply kernels, whose results are rounded to fp16.  silu_f costs two SFU operations per element (ex2 and
-// rcp); at 16 SFU lanes / clk / SM that is 60 us of a 106 us launch on a 128x128x256 tensor at batch 32, i.e. the SFU, not HBM,
-// sets the pace.  Here the reciprocal runs on the FMA pipe instead: integer seed (5 % error) + two Newton steps -> 2^-17, 64x
-// finer than the fp16 rounding of the result, so the kernel is left with ONE SFU operation per element.
-__device__ __forceinline__ float silu_h(float x) {
-  const float d = 1.0f + __expf(-fmaxf(x, -80.0f));                 // finite: d <= 5.6e34
-  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
-  r = r * fmaf(-d, r, 2.0f);
-  r = r * fmaf(-d, r, 2.0f);
-  return x * r;
-}
-
 // Two-term fp16 split of an fp32 value: segment 0 and 2 carry hi = fp16(v), segment 1 carries lo = fp16(v - hi)
 // (network-input channels of the stem conv, see pack_input_kernel).
 __device__ __forceinline__ __half split_term(float v, int seg) {

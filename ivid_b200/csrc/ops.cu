@@ -369,8 +369,7 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.x0 = static_cast<const float*>(d.x0); p.x1 = static_cast<const float*>(d.x1); p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
   p.x0h = d.x0_half ? reinterpret_cast<const __half*>(d.x0) : nullptr;
   p.x1h = d.x0_half ? reinterpret_cast<const __half*>(d.x1) : nullptr;
-  static const bool silu_sfu = getenv("IVID_SILU_SFU") != nullptr;      // previous SiLU (ex2 + rcp on the SFU) for same-box A/B
-  p.silu = d.silu ? (silu_sfu ? 2 : 1) : 0;
+  p.silu = d.silu;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);

@@ -177,3 +177,36 @@ def test_config1_small_model_ddim10_two_steps(golden):
         # DDIM-10 multiplies the eps error by up to 1.6: x_{t-1} <= 1.6 x eps bar
         assert r < 1.6e-3
         xo = ref
+
+
+def test_cli_main_writes_reference_outputs(golden, tmp_path):
+    """`python -m ivid_b200.inference.sample` end to end on tiny models (configs + checkpoints on disk, as the reference CLI
+    consumes them): the directory contract of sample.py:150-176 per view set, scenes loadable by load_scene_views."""
+    import argparse
+    from PIL import Image
+    from ivid_b200.inference import load_scene_views
+    from ivid_b200.inference.sample import main
+    paths = {}
+    for tag, fw_name, seed in (("tiny", "ClassifierFreeGuidance", 1234), ("tiny_cond", "InpaintCFG", 4321)):
+        cfg = json.loads(bytes(golden[f"{tag}_cfg"]).decode())
+        cj = {"backbone": {"name": "AdmUnet2d", "args": cfg}, "framework": {"name": fw_name, "args": {"timesteps": 1000, "beta_schedule": "linear"}}}
+        cp = os.path.join(tmp_path, f"{tag}.json"); json.dump(cj, open(cp, "w"))
+        kp = os.path.join(tmp_path, f"{tag}.pt"); torch.save(unet_ref.make_synthetic_state_dict(cfg, seed=seed), kp)
+        paths[tag] = (cp, kp)
+    for viewset, expect in (("uncond", {"results": 2, "scenes": 2, "grids": 0, "conds": 0}),
+                            ("random", {"results": 2, "scenes": 0, "grids": 2, "conds": 2}),
+                            ("3x9", {"results": 0, "scenes": 2, "grids": 4, "conds": 4})):
+        opt = argparse.Namespace(config_uncond=paths["tiny"][0], ckpt_uncond=paths["tiny"][1], config_cond=paths["tiny_cond"][0],
+                                 ckpt_cond=paths["tiny_cond"][1], output_dir=os.path.join(tmp_path, "out"), seeds="3-4", num_samples=None,
+                                 classes="mod", viewset=viewset, steps_uncond=4, steps_cond=2, guidance=0.5, batchsize=2, fov=45, near=0.6,
+                                 far=5, atol=0.03, rtol=0.03, erode_rgb=3, rng="torch")
+        main(0, 1, opt)
+        out = os.path.join(tmp_path, "out", f"viewset_{viewset}_steps_u4_c2_guidance0.5")
+        for sub, n in expect.items():
+            files = sorted(os.listdir(os.path.join(out, sub)))
+            assert len(files) == n, (viewset, sub, files)
+        if viewset == "3x9":
+            assert Image.open(os.path.join(out, "grids", "rgb_class003_seed00003.png")).size == (9 * 34 + 2, 3 * 34 + 2)
+            assert len(load_scene_views(os.path.join(out, "scenes", "scene_class004_seed00004.npz"))) == 27
+        if viewset == "random":
+            assert Image.open(os.path.join(out, "results", "rgb_class003_seed00003.png")).size == (32, 32)
