@@ -144,22 +144,19 @@ def seconds_per_batch(wl, t_u, t_c, t_warp):
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle port of the reference path (the Python reference cannot travel)
 # ----------------------------------------------------------------------------------------------------------------------
-def pick_threads():
-    """Thread count that is actually fastest for a UNet-sized convolution on this host (oversubscribed SMT threads slow
-    oneDNN down).  Called before any timed CPU work, with warm-up."""
+def pick_threads(unit):
+    """Thread count that is actually fastest for `unit()` (one UNet forward of the configuration's first network at batch 1) on
+    this host: oversubscribed SMT threads slow oneDNN down, and a single-conv probe is too noisy (it picked 16 in one process
+    and 32 in the next on the same box, a 1.6x difference in the result).  One warm run + two timed runs per candidate."""
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    probe_x = torch.randn(1, 256, 128, 128)
-    probe_w = torch.randn(256, 256, 3, 3)
     best, cores = None, 1
-    for nt in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+    for nt in sorted({min(avail, c) for c in (8, 16, 32, 64)}):
         torch.set_num_threads(nt)
-        for _ in range(2):
-            torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
+        unit()
         t0 = time.perf_counter()
-        for _ in range(4):
-            torch.nn.functional.conv2d(probe_x, probe_w, padding=1)
+        unit(); unit()
         dt = time.perf_counter() - t0
-        if best is None or dt < best * 0.95:       # prefer fewer threads unless clearly faster
+        if best is None or dt < best * 0.93:       # prefer fewer threads unless clearly faster
             best, cores = dt, nt
     torch.set_num_threads(cores)
     return cores
@@ -171,10 +168,10 @@ def cpu_reference(config, steps, warmup, budget_s):
     aggregate_conditions) per distinct source count.  Returns (samples_per_s, description dict)."""
     from oracle import sampler_ref, unet_ref
     wl = WORKLOADS[config]
-    cores = pick_threads()
     tb = sampler_ref.Tables(sampler_ref.get_betas("linear", 1000))
     g = torch.Generator().manual_seed(0)
     phases = [k for k in ("uncond", "cond") if wl[k]]
+    cores = None
     per_phase_budget = budget_s * (0.85 if wl["views"] == 1 else 0.7) / len(phases)
     times, counts = {}, {}
     for ph in phases:
@@ -185,6 +182,9 @@ def cpu_reference(config, steps, warmup, budget_s):
         S = cfg["image_size"]
         x = torch.randn(1, 4, S, S, generator=g)
         classes = torch.tensor([7])
+        if cores is None:
+            xin = torch.randn(1, cfg["in_channels"], S, S, generator=g)
+            cores = pick_threads(lambda: model(xin, torch.tensor([500]), classes))
         if key == "Lc":
             y = torch.randn(1, 4, S, S, generator=g); m = (torch.rand(1, 1, S, S, generator=g) > 0.3).float()
         elif key == "SR":
@@ -317,7 +317,7 @@ def main():
     # thread probe and the warm-up steps see an idle host
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, desc = cpu_reference(args.config, 3, 2, budget_s=45.0)
+        v, desc = cpu_reference(args.config, 5, 3, budget_s=60.0)      # same procedure and sample as `--impl reference --steps 5 --warmup 3`
         cpu = {"value": v, "unit": "samples/s", "cores": desc["cores"], "kind": "port", "sample": desc["sample"]}
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"

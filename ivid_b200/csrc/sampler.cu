@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "sampler.cuh"
 
@@ -198,11 +199,9 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   // in-kernel noise of the conditional inputs: Philox(seed', step) with the step read from the device-resident step state
   // (not passed by value: consecutive steps then replay the same CUDA graph of the forward)
   if (cond.kind != 0 && cond.noise_dev == nullptr) { cond.seed = a.seed ^ 0x9E3779B97F4A7C15ull; cond.stream_id = 0; }
-  unet.set_cond_stream_dev(cond.kind != 0 && cond.noise_dev == nullptr ? &reinterpret_cast<StepState*>(d_state_)->stream : nullptr);
-  unet.forward(x_t, N, cond.kind ? &cond : nullptr, d_t_, cls, d_eps_, Nf, stream);
-  unet.set_cond_stream_dev(nullptr);
 
   StepParams p;
+  std::memset(&p, 0, sizeof(p));         // padding bytes are part of the fused route's graph key
   p.x_t = x_t; p.eps = d_eps_; p.noise = a.step_noise_dev; p.x_prev = x_prev; p.pred_x0 = pred_x0;
   p.table = reinterpret_cast<const StepCoef*>(d_table_);
   p.t_index = &reinterpret_cast<StepState*>(d_state_)->t_index;
@@ -222,14 +221,47 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   IVID_REQUIRE(g.depth == nullptr || g.depth_mask != nullptr, "replace_depth needs its mask");
   IVID_REQUIRE(g.convex == nullptr || g.depth != nullptr, "constrain_depth is applied inside replace_depth (ddim.py:90-95)");
   IVID_REQUIRE(!ddim ? (g.rgb == nullptr && g.depth == nullptr) : true, "replace/constrain guidance is DDIM-only");
-  const size_t total4 = static_cast<size_t>(N) * C * HW / 4;
-  const int grid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));
   // strength <= 0: the reference returns (1 + strength) * eps_c without the null-class forward
   // (classifier_free_guidance.py:40-41); only strength == 0 (plain eps_c) is on this path.
   if (scale_only && a.strength != 0.0f)
     throw Error(kErrNotImplemented, "classifier-free guidance with strength < 0 is not supported");
-  if (ddim) ddim_step_kernel<<<std::max(grid, 1), 256, 0, stream>>>(p);
-  else ddpm_step_kernel<<<std::max(grid, 1), 256, 0, stream>>>(p);
+
+  unet.set_cond_stream_dev(cond.kind != 0 && cond.noise_dev == nullptr ? &reinterpret_cast<StepState*>(d_state_)->stream : nullptr);
+  // Fused route: the output head's last kernel IS the step (head_step_kernel): eps never reaches HBM and the update is the last
+  // node of the forward's CUDA graph.  Not taken when per-step pointers change every step (injected noise / trajectories inside
+  // run(): every step would need its own graph) or when the model has no tap-column head.
+  static const bool fuse_ok = getenv("IVID_NO_FUSED_STEP") == nullptr;
+  const bool fuse = fuse_ok && !no_fuse_ && unet.can_fuse_head() && C == 4 && S % 4 == 0;
+  if (fuse) {
+    p.eps = nullptr;
+    HeadStepParams hp;
+    std::memset(&hp, 0, sizeof(hp));
+    hp.sp = p; hp.H = S; hp.W = S;
+    HeadHook hook;
+    uint64_t h = 1469598103934665603ull ^ (ddim ? 0x9E37ull : 0ull);         // FNV-1a over everything the launcher bakes in
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(&p);
+    for (size_t i = 0; i < sizeof(StepParams); ++i) { h ^= bytes[i]; h *= 1099511628211ull; }
+    hook.key = h | 1ull;
+    hook.launch = [hp, ddim](const float* Y, const float* bias, int, int H, int W, int Co, int ldy, cudaStream_t st) mutable {
+      IVID_REQUIRE(Co == 4 && W % 4 == 0, "fused head step: 4 output channels, width % 4 == 0");
+      HeadStepParams q = hp;
+      q.Y = Y; q.bias = bias; q.H = H; q.W = W; q.ldy = ldy;
+      const size_t groups = static_cast<size_t>(q.sp.N) * H * (W / 4);
+      const int grid = static_cast<int>(std::min<size_t>((groups + 255) / 256, static_cast<size_t>(sm_count()) * 8));
+      if (ddim) head_step_kernel<true><<<std::max(grid, 1), 256, 0, st>>>(q);
+      else head_step_kernel<false><<<std::max(grid, 1), 256, 0, st>>>(q);
+      IVID_CHECK_CUDA(cudaGetLastError());
+    };
+    unet.forward(x_t, N, cond.kind ? &cond : nullptr, d_t_, cls, nullptr, Nf, stream, &hook);
+    unet.set_cond_stream_dev(nullptr);
+    return;
+  }
+  unet.forward(x_t, N, cond.kind ? &cond : nullptr, d_t_, cls, d_eps_, Nf, stream);
+  unet.set_cond_stream_dev(nullptr);
+  const size_t total4 = static_cast<size_t>(N) * C * HW / 4;
+  const int grid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(sm_count()) * 8));
+  if (ddim) step_kernel<true><<<std::max(grid, 1), 256, 0, stream>>>(p);
+  else step_kernel<false><<<std::max(grid, 1), 256, 0, stream>>>(p);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 
@@ -247,7 +279,8 @@ void Sampler::run(Unet& unet, float* x, int N, int steps, const ivid_step_args_t
   int cur = 0;
   // per denoising step the host then issues three calls: the step-state kernel, ONE CUDA-graph launch (the whole batch-2N
   // forward) and the fused guidance-mix + x_{t-1} update
-  struct Ready { Sampler* s; ~Ready() { s->classes2_ready_ = false; } } ready_guard{this};
+  struct Ready { Sampler* s; ~Ready() { s->classes2_ready_ = false; s->no_fuse_ = false; } } ready_guard{this};
+  no_fuse_ = noise_all != nullptr || cond_noise_all != nullptr || traj_x0 != nullptr || traj_xt != nullptr;
   if (a.use_cfg && a.classes_dev != nullptr && a.strength > 0.0f) {
     fill_classes_kernel<<<1, 256, 0, stream>>>(a.classes_dev, d_classes2_, N);
     IVID_CHECK_CUDA(cudaGetLastError());

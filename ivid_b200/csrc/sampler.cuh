@@ -80,11 +80,16 @@ struct StepParams {
   GuideParams g;
 };
 
+// (1 + strength) * eps_c - strength * eps_u (only evaluated with strength > 0).  Every product / sum of the step arithmetic is
+// written with explicit round-to-nearest intrinsics (no compiler-chosen FMA contraction), so that step_kernel and
+// head_step_kernel - the same formulas inlined into different kernels - produce identical bits.
+__device__ __forceinline__ float cfg_mix(float ec, float eu, float strength) {
+  return __fsub_rn(__fmul_rn(__fadd_rn(1.0f, strength), ec), __fmul_rn(strength, eu));
+}
 __device__ __forceinline__ float mix_eps(const StepParams& p, size_t i, size_t total) {
   const float ec = p.eps[i];
   if (!p.cfg) return ec;
-  // (1 + strength) * eps_c - strength * eps_u     (only evaluated with strength > 0)
-  return (1.0f + p.strength) * ec - p.strength * p.eps[total + i];
+  return cfg_mix(ec, p.eps[total + i], p.strength);
 }
 
 // classifier-free-guidance mix alone (framework.model_inference): out = (1+s)*eps[0:n) - s*eps[n:2n)
@@ -99,96 +104,160 @@ __global__ void __launch_bounds__(256) cfg_mix_kernel(const float* __restrict__ 
   }
 }
 
-// one thread = 4 consecutive pixels of one (n, c) plane
-__global__ void __launch_bounds__(256) ddpm_step_kernel(const StepParams p) {
-  const size_t total = static_cast<size_t>(p.N) * p.C * p.HW;
-  const StepCoef k = p.table[*p.t_index];
-  const float nz = (*p.t_index != 0) ? 1.0f : 0.0f;
-  const float sd = expf(0.5f * k.post_logvar);
-  const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
-  for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 * 4 < total;
-       i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t i = i4 * 4;
-    float z[4];
-    if (p.noise != nullptr) {
-      const float4 t = ldg_f4(p.noise + i);
-      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-    } else {
-      const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(i4));
-      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-    }
-    float xo[4], x0o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xt = p.x_t[i + j];
-      const float e = mix_eps(p, i + j, total);
-      float x0 = k.sqrt_recip_acp * xt - k.sqrt_recipm1_acp * e;
-      if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-      const float mean = k.post_mean_coef1 * x0 + k.post_mean_coef2 * xt;
-      xo[j] = mean + nz * sd * z[j];
-      x0o[j] = x0;
-    }
-    stg_f4(p.x_prev + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
-    if (p.pred_x0) stg_f4(p.pred_x0 + i, make_float4(x0o[0], x0o[1], x0o[2], x0o[3]));
+// Per-step scalars derived once per thread from the device-resident step state.
+struct StepScalars {
+  StepCoef k;
+  float nz;          // DDPM: t != 0 ; DDIM: t_prev != 0
+  float sd;          // DDPM: exp(0.5 * posterior_log_variance_clipped)
+  float sigma, c_x0, c_eps;    // DDIM
+  uint32_t stream;
+};
+template <bool kDdim>
+__device__ __forceinline__ StepScalars step_scalars(const StepParams& p) {
+  StepScalars s;
+  s.k = p.table[*p.t_index];
+  s.stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
+  if (!kDdim) {
+    s.nz = (*p.t_index != 0) ? 1.0f : 0.0f;
+    s.sd = expf(__fmul_rn(0.5f, s.k.post_logvar));
+    s.sigma = 0.f; s.c_x0 = 0.f; s.c_eps = 0.f;
+  } else {
+    const int tprev = *p.t_prev;
+    s.nz = (tprev != 0) ? 1.0f : 0.0f;
+    const float ab = s.k.acp;
+    const float abp = (tprev == 0) ? 1.0f : p.table[tprev - 1].acp;   // alphas_cumprod_prev[t_prev]
+    s.sigma = __fmul_rn(__fmul_rn(p.eta, sqrtf(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)))), sqrtf(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+    s.c_x0 = sqrtf(abp);
+    s.c_eps = sqrtf(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(s.sigma, s.sigma)));
+    s.sd = 0.f;
   }
+  return s;
+}
+// x_{t-1} and x_0 of one element (sample n, channel c, pixel pix) from x_t, the (already guidance-mixed) eps and the N(0,1) draw z
+template <bool kDdim>
+__device__ __forceinline__ void step_element(const StepParams& p, const StepScalars& s, int n, int c, size_t pix, float xt, float e, float z,
+                                             float& xo, float& x0o) {
+  const StepCoef& k = s.k;
+  auto mul = [](float a, float b) { return __fmul_rn(a, b); };
+  auto add = [](float a, float b) { return __fadd_rn(a, b); };
+  auto sub = [](float a, float b) { return __fsub_rn(a, b); };
+  float x0 = sub(mul(k.sqrt_recip_acp, xt), mul(k.sqrt_recipm1_acp, e));
+  if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  if (!kDdim) {
+    const float mean = add(mul(k.post_mean_coef1, x0), mul(k.post_mean_coef2, xt));
+    xo = add(mean, mul(mul(s.nz, s.sd), z));
+    x0o = x0;
+    return;
+  }
+  if (c < 3) {
+    if (p.g.rgb != nullptr) {
+      const float y = p.g.rgb[(static_cast<size_t>(n) * 3 + c) * p.HW + pix];
+      const float m = p.g.rgb_mask[static_cast<size_t>(n) * p.HW + pix];
+      x0 = add(mul(sub(1.0f, s.nz), x0), mul(s.nz, add(mul(add(mul(p.g.w_rgb, y), mul(p.g.w_rgb_c, x0)), m), mul(x0, sub(1.0f, m)))));
+    }
+  } else if (p.g.depth != nullptr) {
+    const float y = p.g.depth[static_cast<size_t>(n) * p.HW + pix];
+    const float m = p.g.depth_mask[static_cast<size_t>(n) * p.HW + pix];
+    x0 = add(mul(add(mul(p.g.w_depth, y), mul(p.g.w_depth_c, x0)), m), mul(x0, sub(1.0f, m)));
+    if (p.g.convex != nullptr) {
+      const float cv = p.g.convex[static_cast<size_t>(n) * p.HW + pix];
+      x0 = add(mul(x0, m), mul(add(mul(p.g.w_convex, fmaxf(x0, cv)), mul(p.g.w_convex_c, x0)), sub(1.0f, m)));
+    }
+  }
+  const float e2 = __fdiv_rn(sub(mul(k.sqrt_recip_acp, xt), x0), k.sqrt_recipm1_acp);
+  const float mean = add(mul(s.c_x0, x0), mul(s.c_eps, e2));
+  xo = add(mean, mul(mul(s.nz, s.sigma), z));
+  x0o = x0;
+}
+// the four N(0,1) draws of elements [i, i+4) of the flattened [N,C,H,W] tensor (i % 4 == 0): injected or Philox(seed, stream, i/4)
+__device__ __forceinline__ void step_noise4(const StepParams& p, const StepScalars& s, size_t i, bool needed, float (&z)[4]) {
+  z[0] = z[1] = z[2] = z[3] = 0.f;
+  if (!needed) return;
+  const float4 t = p.noise != nullptr ? ldg_f4(p.noise + i) : philox_normal4(p.seed, s.stream, static_cast<uint32_t>(i >> 2));
+  z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
 }
 
-__global__ void __launch_bounds__(256) ddim_step_kernel(const StepParams p) {
+// one thread = 4 consecutive pixels of one (n, c) plane
+template <bool kDdim>
+__global__ void __launch_bounds__(256) step_kernel(const StepParams p) {
   const size_t total = static_cast<size_t>(p.N) * p.C * p.HW;
-  const StepCoef k = p.table[*p.t_index];
-  const int tprev = *p.t_prev;
-  const float nz = (tprev != 0) ? 1.0f : 0.0f;
-  const float ab = k.acp;
-  const float abp = (tprev == 0) ? 1.0f : p.table[tprev - 1].acp;   // alphas_cumprod_prev[t_prev]
-  const float sigma = p.eta * sqrtf((1.0f - abp) / (1.0f - ab)) * sqrtf(1.0f - ab / abp);
-  const float c_x0 = sqrtf(abp);
-  const float c_eps = sqrtf(1.0f - abp - sigma * sigma);
-  const uint32_t stream = p.stream + (p.stream_dev ? static_cast<uint32_t>(*p.stream_dev) : 0u);
+  const StepScalars s = step_scalars<kDdim>(p);
   for (size_t i4 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i4 * 4 < total;
        i4 += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t i = i4 * 4;
     const int plane = static_cast<int>(i / p.HW);      // n*C + c
     const int n = plane / p.C, c = plane % p.C;
     const size_t pix = i - static_cast<size_t>(plane) * p.HW;
-    float z[4] = {0.f, 0.f, 0.f, 0.f};
-    if (sigma != 0.0f) {
-      if (p.noise != nullptr) {
-        const float4 t = ldg_f4(p.noise + i);
-        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-      } else {
-        const float4 t = philox_normal4(p.seed, stream, static_cast<uint32_t>(i4));
-        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-      }
-    }
+    float z[4];
+    step_noise4(p, s, i, !kDdim || s.sigma != 0.0f, z);
     float xo[4], x0o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xt = p.x_t[i + j];
-      const float e = mix_eps(p, i + j, total);
-      float x0 = k.sqrt_recip_acp * xt - k.sqrt_recipm1_acp * e;
-      if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-      if (c < 3) {
-        if (p.g.rgb != nullptr) {
-          const float y = p.g.rgb[(static_cast<size_t>(n) * 3 + c) * p.HW + pix + j];
-          const float m = p.g.rgb_mask[static_cast<size_t>(n) * p.HW + pix + j];
-          x0 = (1.0f - nz) * x0 + nz * ((p.g.w_rgb * y + p.g.w_rgb_c * x0) * m + x0 * (1.0f - m));
-        }
-      } else if (p.g.depth != nullptr) {
-        const float y = p.g.depth[static_cast<size_t>(n) * p.HW + pix + j];
-        const float m = p.g.depth_mask[static_cast<size_t>(n) * p.HW + pix + j];
-        x0 = (p.g.w_depth * y + p.g.w_depth_c * x0) * m + x0 * (1.0f - m);
-        if (p.g.convex != nullptr) {
-          const float cv = p.g.convex[static_cast<size_t>(n) * p.HW + pix + j];
-          x0 = x0 * m + (p.g.w_convex * fmaxf(x0, cv) + p.g.w_convex_c * x0) * (1.0f - m);
-        }
-      }
-      const float e2 = (k.sqrt_recip_acp * xt - x0) / k.sqrt_recipm1_acp;
-      const float mean = c_x0 * x0 + c_eps * e2;
-      xo[j] = mean + nz * sigma * z[j];
-      x0o[j] = x0;
-    }
+    for (int j = 0; j < 4; ++j) step_element<kDdim>(p, s, n, c, pix + j, p.x_t[i + j], mix_eps(p, i + j, total), z[j], xo[j], x0o[j]);
     stg_f4(p.x_prev + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
     if (p.pred_x0) stg_f4(p.pred_x0 + i, make_float4(x0o[0], x0o[1], x0o[2], x0o[3]));
+  }
+}
+
+// Output head + denoising step in ONE kernel (the last node of the forward's CUDA graph): eps of both guidance halves is formed
+// from the tap columns Y of the output head's 1x1 GEMM (the shift-and-add of eps_gather_kernel, same summation order), mixed, and
+// pushed through the DDPM / DDIM update without ever being written to HBM.  One thread = 4 consecutive pixels (one row segment)
+// of one sample, all Co = 4 channels; noise indices and arithmetic are those of step_kernel, so both routes agree bit for bit.
+struct HeadStepParams {
+  StepParams sp;
+  const float* Y;          // [2N or N][H][W][ldy] tap columns (tap*Co + c)
+  const float* bias;       // [Co]
+  int H, W, ldy;
+};
+__device__ __forceinline__ void head_eps4(const HeadStepParams& h, int n, int y, int x, float (&e)[4]) {
+  e[0] = e[1] = e[2] = e[3] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = y + tap / 3 - 1, ww = x + tap % 3 - 1;
+    if (hh < 0 || hh >= h.H || ww < 0 || ww >= h.W) continue;
+    const float4 v = ldg_f4(h.Y + ((static_cast<size_t>(n) * h.H + hh) * h.W + ww) * h.ldy + tap * 4);
+    e[0] += v.x; e[1] += v.y; e[2] += v.z; e[3] += v.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) e[c] += __ldg(h.bias + c);
+}
+template <bool kDdim>
+__global__ void __launch_bounds__(256) head_step_kernel(const HeadStepParams h) {
+  const StepParams& p = h.sp;
+  const StepScalars s = step_scalars<kDdim>(p);
+  const int w4 = h.W / 4;
+  const size_t groups = static_cast<size_t>(p.N) * h.H * w4;
+  for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < groups; g += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(g % w4);
+    const int y = static_cast<int>((g / w4) % h.H);
+    const int n = static_cast<int>(g / (static_cast<size_t>(w4) * h.H));
+    float e[4][4];                  // [pixel][channel]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ec[4];
+      head_eps4(h, n, y, xg * 4 + j, ec);
+      if (p.cfg) {
+        float eu[4];
+        head_eps4(h, n + p.N, y, xg * 4 + j, eu);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ec[c] = cfg_mix(ec[c], eu[c], p.strength);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e[j][c] = ec[c];
+    }
+    const size_t pix = static_cast<size_t>(y) * h.W + xg * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const size_t i = (static_cast<size_t>(n) * 4 + c) * p.HW + pix;
+      float z[4];
+      step_noise4(p, s, i, !kDdim || s.sigma != 0.0f, z);
+      const float4 xt = ldg_f4(p.x_t + i);
+      const float xtv[4] = {xt.x, xt.y, xt.z, xt.w};
+      float xo[4], x0o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) step_element<kDdim>(p, s, n, c, pix + j, xtv[j], e[j][c], z[j], xo[j], x0o[j]);
+      stg_f4(p.x_prev + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+      if (p.pred_x0) stg_f4(p.pred_x0 + i, make_float4(x0o[0], x0o[1], x0o[2], x0o[3]));
+    }
   }
 }
 

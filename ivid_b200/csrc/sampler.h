@@ -32,6 +32,7 @@ class Sampler {
   int64_t* d_classes2_ = nullptr;
   float* d_eps_ = nullptr;
   float* d_xtmp_ = nullptr;
+  bool no_fuse_ = false;                   // inside run() with per-step noise / trajectory pointers: keep the separate step kernel
   bool classes2_ready_ = false;            // d_classes2_ already holds [classes, -1 ...] for (classes2_src_, classes2_n_)
   const int64_t* classes2_src_ = nullptr;
   int classes2_n_ = 0;

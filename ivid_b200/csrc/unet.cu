@@ -422,6 +422,7 @@ struct Plan {
   // per-call inputs
   const float* x = nullptr; int Nx = 0; ivid_cond_t cond{}; const int64_t* t = nullptr; const int64_t* classes = nullptr;
   float* eps = nullptr;
+  const HeadHook* hook = nullptr;
   const int* cond_stream_dev = nullptr;
   // CUDA graphs of the whole forward (memset + ~215 launches), one per distinct set of per-call pointers / by-value inputs:
   // the launch records bake them in, so a replay is valid exactly when the key matches.
@@ -429,8 +430,9 @@ struct Plan {
     const void* x; int Nx; const void* t; const void* classes; void* eps;
     int kind; const void* y; const void* mask; const void* mask_rgb; const void* noise; uint64_t seed; uint32_t stream_id;
     const void* stream_dev;
+    uint64_t hook_key;
     bool operator==(const GraphKey& o) const {
-      return x == o.x && Nx == o.Nx && t == o.t && classes == o.classes && eps == o.eps && kind == o.kind && y == o.y && mask == o.mask &&
+      return hook_key == o.hook_key && x == o.x && Nx == o.Nx && t == o.t && classes == o.classes && eps == o.eps && kind == o.kind && y == o.y && mask == o.mask &&
              mask_rgb == o.mask_rgb && noise == o.noise && seed == o.seed && stream_id == o.stream_id && stream_dev == o.stream_dev;
     }
   };
@@ -836,7 +838,10 @@ Plan* Unet::build_plan(int N) {
         const float* Y = s_h; const float* ob = Wf(out_conv_.b_off);
         const int Co = cfg_.out_channels;
         pl->ops.tag("eps_gather", 0, static_cast<double>(N) * S * S * (9.0 * Co * 4 + Co * 4));
-        pl->ops.push_back([=](cudaStream_t s) { launch_eps_gather(Y, ob, pl->eps, N, S, S, Co, 64, s); });
+        pl->ops.push_back([=](cudaStream_t s) {
+          if (pl->hook != nullptr) pl->hook->launch(Y, ob, N, S, S, Co, 64, s);
+          else launch_eps_gather(Y, ob, pl->eps, N, S, S, Co, 64, s);
+        });
       }
     } else if (create) {
       ConvDesc d;
@@ -867,8 +872,12 @@ Plan* Unet::build_plan(int N) {
   return plan.release();
 }
 
+bool Unet::can_fuse_head() const {
+  return out_split_ && conv_can_out16(final_ch_) && cfg_.out_channels == 4 && cfg_.image_size % 4 == 0;
+}
+
 void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_t* t, const int64_t* classes, float* eps,
-                   int N, cudaStream_t stream) {
+                   int N, cudaStream_t stream, const HeadHook* hook) {
   if (!finalized()) throw Error(kErrState, "AdmUnet2d: forward before .cuda()/finalize");
   IVID_REQUIRE(N >= 1 && Nx >= 1 && N % Nx == 0, "forward: N must be a positive multiple of Nx");
   // reference: "this model is not class-conditioned" (adm.py:540)
@@ -877,6 +886,8 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   ivid_cond_t cnd = cond ? *cond : ivid_cond_t{};
   const int expect_in = cnd.kind == 1 ? (cnd.mask_rgb_dev ? 10 : 9) : (cnd.kind == 2 ? 8 : cfg_.in_channels);
   IVID_REQUIRE(expect_in == cfg_.in_channels, "forward: conditional inputs do not match the model's in_channels");
+  IVID_REQUIRE(hook == nullptr || can_fuse_head(), "forward: a head hook needs the tap-column output head");
+  IVID_REQUIRE(hook != nullptr || eps != nullptr, "forward: eps output missing");
 
   // Two half-batches on two streams: the HBM-bound GroupNorm passes of one half overlap the tensor-bound convolutions
   // of the other (a persistent conv CTA leaves enough registers / shared memory on every SM for a gn_apply block).
@@ -885,7 +896,7 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   // 0.08 ms = 0.28 ms when issued concurrently), so the split is opt-in (IVID_SPLIT_BATCH=1) until the co-residency
   // blocker is understood.
   static const bool split_ok = getenv("IVID_SPLIT_BATCH") != nullptr;
-  const bool can_split = split_ok && !profile_ && N % 2 == 0 && N >= 4 && (Nx == N || Nx == N / 2) &&
+  const bool can_split = split_ok && hook == nullptr && !profile_ && N % 2 == 0 && N >= 4 && (Nx == N || Nx == N / 2) &&
                          !(cnd.kind != 0 && Nx == N && cnd.noise_dev == nullptr);
   if (can_split) {
     const int half = N / 2;
@@ -928,6 +939,7 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
   pl->x = x; pl->Nx = Nx; pl->t = t; pl->classes = classes; pl->eps = eps;
   pl->cond = cnd;
   pl->cond_stream_dev = cond_stream_dev_;
+  pl->hook = hook;
   if (!profile_) {
     // The first call of a plan runs eagerly (one-time function attributes, module loading); from the second call on the
     // forward is ONE cudaGraphLaunch.  Graphs are captured on a private stream (the caller's may be the legacy default
@@ -936,7 +948,8 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
     ++pl->runs;
     if (graphs_on && pl->runs > 1) {
       const Plan::GraphKey key{x, Nx, t, classes, eps, cnd.kind, cnd.y_dev, cnd.mask_dev, cnd.mask_rgb_dev, cnd.noise_dev,
-                               cnd.kind != 0 ? cnd.seed : 0ull, cnd.kind != 0 ? cnd.stream_id : 0u, cond_stream_dev_};
+                               cnd.kind != 0 ? cnd.seed : 0ull, cnd.kind != 0 ? cnd.stream_id : 0u, cond_stream_dev_,
+                               hook ? hook->key : 0ull};
       for (auto& g : pl->graphs)
         if (g.key == key) {
           g.last_use = pl->runs;
@@ -959,7 +972,7 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
       const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       IVID_CHECK_CUDA(ie);
-      if (pl->graphs.size() >= 8) {
+      if (pl->graphs.size() >= 16) {
         // evict the least recently used graph; it may still be executing on the caller's stream
         size_t victim = 0;
         for (size_t i = 1; i < pl->graphs.size(); ++i) if (pl->graphs[i].last_use < pl->graphs[victim].last_use) victim = i;

@@ -63,6 +63,15 @@ struct BlockDef { std::vector<LayerRef> layers; bool is_input = false; bool is_o
 
 struct Plan;
 
+// Optional replacement of the output head's last kernel (eps_gather_kernel): the sampler hands the forward a launcher that
+// consumes the tap columns Y directly (head_step_kernel: eps of both guidance halves -> mix -> x_{t-1}), so that eps never
+// goes to HBM and the update is the last node of the forward's CUDA graph.  `key` must change whenever anything the launcher
+// bakes in (pointers, scalars) changes: it is part of the graph-cache key.
+struct HeadHook {
+  std::function<void(const float* Y, const float* bias, int N, int H, int W, int Co, int ldy, cudaStream_t s)> launch;
+  uint64_t key = 0;
+};
+
 class Unet {
  public:
   explicit Unet(const std::string& cfg_json);
@@ -79,7 +88,9 @@ class Unet {
 
   // forward over a batch of N samples; x rows are read modulo Nx (CFG halves share x)
   void forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_t* t, const int64_t* classes, float* eps,
-               int N, cudaStream_t stream);
+               int N, cudaStream_t stream, const HeadHook* hook = nullptr);
+  // whether the output head runs as the tap-column GEMM whose last kernel a HeadHook can replace
+  bool can_fuse_head() const;
   // Device-resident Philox stream id (step counter) of the conditional-input noise: the sampler points this at its step
   // state so that consecutive denoising steps replay the same CUDA graph (a by-value stream id would change the key).
   void set_cond_stream_dev(const int* p) { cond_stream_dev_ = p; }

@@ -146,3 +146,23 @@ def test_superres_ddim_step_vs_oracle(golden):
     got = fw.model_inference(x.cuda(), torch.tensor([499, 499]).cuda(), y.cuda(), classes.cuda(), strength=3.0)
     ref_eps = sampler_ref.cond_eps(model, sampler_ref.make_sr_inputs(x, y), torch.tensor([499, 499]), classes, 3.0)
     assert G.report("superres model_inference", got, ref_eps) < 3.5e-3                    # guidance 3.0: see test_framework_model_inference_cfg
+
+
+def test_fused_head_step_equals_separate_step_kernel(golden):
+    """The production loop ends every forward in head_step_kernel (output-head shift-and-add + guidance mix + x_{t-1} update,
+    last node of the forward's CUDA graph); with return_trajectory=True the per-step pointers change every step and the loop
+    falls back to eps_gather_kernel + step_kernel.  Same Philox draws (same torch seed) -> the two routes must agree."""
+    cfg = _cfg(golden, "tiny")
+    fw = frameworks.ClassifierFreeGuidance(_net(cfg, 1234), timesteps=1000, beta_schedule="linear")
+    rng = np.random.default_rng(2)
+    x = torch.from_numpy(rng.standard_normal((2, 4, 32, 32)).astype(np.float32)).cuda()
+    classes = torch.tensor([1, 2]).cuda()
+    for s, kw in ((samplers.DdimSampler(fw), dict(steps=8, eta=1.0)), (samplers.DdpmSampler(fw), dict())):
+        torch.manual_seed(5)
+        a = s.sample(2, noise=x, classes=classes, strength=0.5, verbose=False, **kw).samples
+        torch.manual_seed(5)
+        b = s.sample(2, noise=x, classes=classes, strength=0.5, verbose=False, return_trajectory=True, **kw)
+        G.report(f"{type(s).__name__}: fused head+step vs separate kernels", a, b.samples)
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b.samples), "the step arithmetic is pinned (explicit rn intrinsics): both routes give the same bits"
+        assert torch.equal(b.pred_x_t[-1], b.samples)
