@@ -251,7 +251,7 @@ def cpu_reference(config, steps, warmup, budget_s):
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    value, desc = cpu_reference(args.config, args.steps, max(args.warmup, 1), budget_s=150.0)
+    value, desc = cpu_reference(args.config, args.steps, max(args.warmup, 1), budget_s=120.0)
     wl = WORKLOADS[args.config]
     line = {
         "impl": "reference", "metric": "128x128 RGBD multiview samples/sec", "value": value, "unit": "samples/s",
@@ -317,7 +317,7 @@ def main():
     # thread probe and the warm-up steps see an idle host
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, desc = cpu_reference(args.config, 5, 3, budget_s=60.0)      # same procedure and sample as `--impl reference --steps 5 --warmup 3`
+        v, desc = cpu_reference(args.config, 5, 3, budget_s=120.0)     # same procedure and sample as `--impl reference --steps 5 --warmup 3`
         cpu = {"value": v, "unit": "samples/s", "cores": desc["cores"], "kind": "port", "sample": desc["sample"]}
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"

@@ -29,7 +29,16 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_wrapped(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // previous form (A/B: IVID_SILU_WRAPPED)
+// x * sigmoid(x) with the two SFU approximations issued directly: __expf / __fdividef wrap the same ex2.approx / rcp.approx in
+// range fix-ups (an FSETP, two predicated FMULs and a branch per call) that matter in the GroupNorm-apply kernels, where SiLU
+// is most of the arithmetic.  x -> -inf: e = +inf, rcp = 0, result -0; x -> +inf: e = 0, result x.
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 // Two-term fp16 split of an fp32 value: segment 0 and 2 carry hi = fp16(v), segment 1 carries lo = fp16(v - hi)
 // (network-input channels of the stem conv, see pack_input_kernel).

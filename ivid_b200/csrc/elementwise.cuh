@@ -94,7 +94,7 @@ struct GnApplyParams {
   int C0, C1;
   int N, H, W;                          // INPUT spatial size
   int mode;                             // 0 same, 1 up, 2 down
-  int silu;
+  int silu;                             // 0 none, 1 SiLU (silu_f), 2 SiLU through __expf / __fdividef (same-box A/B)
   const double* stats0; const double* stats1;   // [N][C0][2], [N][C1][2] (sum, sum of squares over H*W)
   int groups; double inv_count; float eps;
   const float* gamma; const float* beta;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float y = fmaf(raw[j], s_ab[j * c8 + cg], s_ab[C + j * c8 + cg]);
-        if (p.silu) y = silu_f(y);
+        if (p.silu) y = (p.silu == 1) ? silu_f(y) : silu_wrapped(y);
         act[j] = y;
       }
       uint4 pk;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float y = fmaf(raw[u][j], s_ab[j * c8 + cg], s_ab[C + j * c8 + cg]);
-          if (p.silu) y = silu_f(y);
+          if (p.silu) y = (p.silu == 1) ? silu_f(y) : silu_wrapped(y);
           act[j] = y;
         }
         uint4 pk;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float y = fmaf(v[j], A[j], B[j]);
-            if (p.silu) y = silu_f(y);
+            if (p.silu) y = (p.silu == 1) ? silu_f(y) : silu_wrapped(y);
             act[j] += y;
             raw[j] += v[j];
           }
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float y = fmaf(raw[j], A[j], B[j]);
-        if (p.silu) y = silu_f(y);
+        if (p.silu) y = (p.silu == 1) ? silu_f(y) : silu_wrapped(y);
         act[j] = y;
       }
     }
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
         y0 = fmaf(f.x, s_ab[(2 * j) * c8 + cg], s_ab[C + (2 * j) * c8 + cg]);
         y1 = fmaf(f.y, s_ab[(2 * j + 1) * c8 + cg], s_ab[C + (2 * j + 1) * c8 + cg]);
       }
-      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      if (p.silu) { y0 = (p.silu == 1) ? silu_f(y0) : silu_wrapped(y0); y1 = (p.silu == 1) ? silu_f(y1) : silu_wrapped(y1); }
       pk[j] = pack_h2(y0, y1);
       if (kLo) {
         const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&pk[j]));
@@ -490,29 +490,39 @@ __global__ void __launch_bounds__(256, 3) gn_apply_h16_kernel(const GnApplyParam
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int N,
                                                          int Nx, int Cin, int HW) {
-  const size_t total = static_cast<size_t>(N) * HW * 8;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx & 7);
-    const size_t pixn = idx >> 3;
-    const int n = static_cast<int>(pixn / HW);
-    const int p = static_cast<int>(pixn % HW);
-    const float* src = x + (static_cast<size_t>(n % Nx) * Cin) * HW + p;
-    uint32_t w[4];
+  // phase 1: one thread per pixel reads its Cin fp32 values (coalesced along the pixel index of every channel plane);
+  // phase 2: the block writes the 64 fp16 operand channels with 16-byte coalesced stores, one thread per (pixel, 8-channel group)
+  __shared__ float s_ch[256][17];
+  const size_t total = static_cast<size_t>(N) * HW;
+  for (size_t base = blockIdx.x * static_cast<size_t>(blockDim.x); base < total; base += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t idx = base + threadIdx.x;
+    if (idx < total) {
+      const int n = static_cast<int>(idx / HW);
+      const int p = static_cast<int>(idx % HW);
+      const float* src = x + (static_cast<size_t>(n % Nx) * Cin) * HW + p;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      __half2 h2;
-      __half e[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int oc = g * 8 + 2 * k + q;
-        const int seg = oc / Cin;
-        e[q] = seg < 3 ? split_term(__ldg(src + static_cast<size_t>(oc - seg * Cin) * HW), seg) : __float2half_rn(0.f);
-      }
-      h2 = __halves2half2(e[0], e[1]);
-      w[k] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int c = 0; c < 16; ++c) s_ch[threadIdx.x][c] = c < Cin ? __ldg(src + static_cast<size_t>(c) * HW) : 0.f;
     }
-    *reinterpret_cast<uint4*>(out + pixn * 64 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    __syncthreads();
+    const int live = static_cast<int>(min(static_cast<size_t>(256), total - base));
+    for (int it = threadIdx.x; it < live * 8; it += 256) {
+      const int px = it >> 3, g = it & 7;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half e[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int oc = g * 8 + 2 * k + q;
+          const int seg = oc / Cin;
+          e[q] = seg < 3 ? split_term(s_ch[px][oc - seg * Cin], seg) : __float2half_rn(0.f);
+        }
+        const __half2 h2 = __halves2half2(e[0], e[1]);
+        w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(out + (base + px) * 64 + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
   }
 }
 

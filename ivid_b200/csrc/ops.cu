@@ -369,7 +369,8 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.x0 = static_cast<const float*>(d.x0); p.x1 = static_cast<const float*>(d.x1); p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W; p.mode = d.mode;
   p.x0h = d.x0_half ? reinterpret_cast<const __half*>(d.x0) : nullptr;
   p.x1h = d.x0_half ? reinterpret_cast<const __half*>(d.x1) : nullptr;
-  p.silu = d.silu;
+  static const bool silu_wrapped = getenv("IVID_SILU_WRAPPED") != nullptr;
+  p.silu = d.silu ? (silu_wrapped ? 2 : 1) : 0;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);
@@ -410,9 +411,8 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
 }
 
 void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s) {
-  IVID_REQUIRE(Cin <= 16, "pack_input: at most 16 input channels");
-  IVID_REQUIRE(Cin >= 1 && 3 * Cin <= 64, "pack_input: the two-term split needs 3*Cin <= 64 operand channels");
-  pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW * 8, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,
+  IVID_REQUIRE(Cin >= 1 && Cin <= 16, "pack_input: 1..16 input channels (two-term split inside 64 operand channels)");
+  pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,
                                                                                  Cin, HW);
   IVID_CHECK_CUDA(cudaGetLastError());
 }
