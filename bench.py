@@ -90,16 +90,19 @@ def synth_rgbd(rng, n=128):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons.  The process is started BEFORE the warm-up (nvidia-smi needs ~0.2 s to
+    deliver its first row) and every row is stamped when it arrives; `stop()` keeps the rows that fall inside the timed region
+    marked by `mark_start()` .. `stop()` (short regions: the rows closest to it)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -108,18 +111,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.perf_counter()
+        time.sleep(0.12)                      # let the row that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.12]
+        if not inside and self.rows:          # region shorter than the sampling period: the rows nearest to it
+            inside = [r for (t, r) in sorted(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[:2]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
@@ -424,6 +436,9 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     # ---- warm-up ----
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
     xu = xc = x
     for i in range(args.warmup):
         if args.full:
@@ -432,10 +447,9 @@ def main():
             if s_u: xu = step_u(xu, i)
             if s_c: xc = step_c(xc, i)
     # ---- timed region: K steps ----
-    clocks = ClockSampler(local) if rank == 0 else None
     barrier()
     if clocks:
-        clocks.start()
+        clocks.mark_start()
     e0, e1 = ev(), ev()
     marks = []
     e0.record()
