@@ -63,7 +63,8 @@ int ivid_unet_forward(ivid_unet_t* h, const float* x_dev, int Nx, const int64_t*
                       float* eps_dev, int N, void* stream);
 
 /* Parity aid (per-layer taps, tests/test_gpu_unet.py): output of the module `layer` (reference module path such as
- * "input_blocks.3.0", "middle_block.1", "output_blocks.14.0"; the stem is "input_blocks.0.0") of the LAST forward of batch
+ * "input_blocks.3.0", "middle_block.1", "output_blocks.14.0"; the stem is "input_blocks.0.0"; "emb" = time + class embedding
+ * [N, 4*model_channels, 1, 1]; "film" = the stacked emb_layers outputs of all ResBlocks) of the LAST forward of batch
  * N, as fp32 NCHW on the host.  host_out == NULL only queries the shape.  Synchronises the device. */
 int ivid_unet_debug_tap(ivid_unet_t* h, int N, const char* layer, float* host_out, uint64_t capacity, int* C, int* H, int* W);
 
@@ -218,7 +219,8 @@ int ivid_warp_resolve_frame(ivid_warp_t* w, double project_near, double project_
 int ivid_warp_render_simple(ivid_warp_t* w, const float* verts_host, int nverts, const uint32_t* faces_host, int nfaces,
                             const float* color_host, const float* target_mv_host, double fov_deg, float* color_out_host,
                             float* depth_out_host, float* mask_out_host, void* stream);
-/* forward_backward_warp for every sample of the handle's batch, device resident between the two renders:
+/* forward_backward_warp for every sample of the handle's batch, device resident between the two renders (uses view slots 0 and
+ * 1 of the handle and forgets any source views it held, like ivid_warp_reset):
  *   lin_depth0_host [batch,H,W] = linearize_depth(rgbd[..., 3:], near, far), color0_host [batch,H,W,3] = rgbd[..., :3];
  *   mv1 / mv0 [batch][16] (or one shared matrix each); params: padding (of the first mesh), fov, near, far, atol, rtol;
  *   out_host [batch,7,H,W]: color(3), depth, mask, mask, projected depth before masking. */

@@ -442,6 +442,7 @@ struct Plan {
   std::vector<Tap> taps;
   std::vector<GraphEntry> graphs;
   uint64_t runs = 0;
+  uint64_t graph_hits = 0, graph_captures = 0;      // a caller whose pointers change on every call gains nothing from capturing
   ~Plan() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     for (auto* c : convs) conv_launch_destroy(c);
@@ -656,6 +657,8 @@ Plan* Unet::build_plan(int N) {
         launch_linear(s_pe, w1, b1, s_e1, N, mc, E, 0, nullptr, nullptr, 1, s);
         launch_linear(s_e1, w2, b2, s_emb, N, E, E, 1, pl->classes ? lab : nullptr, pl->classes, N, s);
       });
+      pl->taps.push_back({"emb", s_emb, nullptr, E, 1, 1});                 // time (+ class) embedding [N, E] (adm.py:545-555)
+      pl->taps.push_back({"film", s_film, nullptr, FT, 1, 1});              // all emb_layers outputs [N, sum 2*Cout] (adm.py:174-177, 214)
       pl->ops.tag("embed", 2.0 * N * E * FT, 4.0 * E * FT, "film table O=" + std::to_string(FT));
       pl->ops.push_back([=](cudaStream_t s) {
         if (E % 32 == 0) launch_film_table(s_emb, wf, bf, s_xt, s_film, N, E, FT, s);
@@ -953,9 +956,19 @@ void Unet::forward(const float* x, int Nx, const ivid_cond_t* cond, const int64_
       for (auto& g : pl->graphs)
         if (g.key == key) {
           g.last_use = pl->runs;
+          ++pl->graph_hits;
           IVID_CHECK_CUDA(cudaGraphLaunch(g.exec, stream));
           return;
         }
+      // capture pays off when keys repeat (the sampler loop: 2 keys); if 32 captures saw fewer hits than captures the caller
+      // hands fresh buffers to every call (e.g. a Python loop that keeps every x_{t-1}): replay the launches on the stream
+      const bool thrash = pl->graph_captures >= 32 && pl->graph_hits < pl->graph_captures;
+      if (thrash) {
+        IVID_CHECK_CUDA(cudaMemsetAsync(pl->stats_base, 0, pl->stats_bytes, stream));
+        for (auto& op : pl->ops.v) op.fn(stream);
+        return;
+      }
+      ++pl->graph_captures;
       if (cap_stream_ == nullptr) IVID_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
       IVID_CHECK_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeRelaxed));

@@ -144,7 +144,37 @@ def test_layerwise_taps(golden, which):
         print(f"[tap] {which:5s} {name:24s} {tuple(want.shape)!s:22s} rel {r:.3e}")
         if r > worst:
             worst, worst_name = r, name
+    # PosEncoding -> time_embed (+ label_emb, null class -> zeros) is fp32 end to end (adm.py:11-33,357-365,545-555)
+    r_emb = G.rel(_tap(net, 1, "emb")[:, :, 0, 0], taps["emb"])
+    print(f"[tap] {which:5s} emb (time + class embedding) rel {r_emb:.3e}")
+    assert r_emb < 2e-6
     # the stem carries a two-term split of x and W: it must be far inside fp16 precision
     assert G.rel(_tap(net, 1, "input_blocks.0.0"), taps["input_blocks.0.0"]) < 2e-5
     assert worst < 1.2e-3, f"layer {worst_name} is {worst:.3e} from the oracle"
     _check(f"{which} taps run eps", got, ref, cfg, sd, x, t, c)
+
+
+def test_embeddings_and_film_table_fp32(golden):
+    """PosEncoding / time_embed / label_emb incl. the null class, and the stacked emb_layers ("FiLM table") of every ResBlock,
+    against the oracle in fp32."""
+    import torch.nn.functional as F
+    cfg = json.loads(bytes(golden["tiny_cfg"]).decode())
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
+    net = _load(cfg, sd)
+    x = torch.zeros(3, 4, 32, 32)
+    t = torch.tensor([999, 0, 421]); c = torch.tensor([9, -1, 0])
+    taps = {}
+    unet_ref.unet_forward(cfg, sd, x, t, c, taps=taps)
+    net(x.cuda(), t.cuda(), c.cuda())
+    emb = _tap(net, 3, "emb")[:, :, 0, 0]
+    assert G.report("emb [N, 4*mc] (t = 999 / 0 / 421, classes 9 / null / 0)", emb, taps["emb"]) < 2e-6
+    blocks, _ = unet_ref._topology(cfg)
+    want = torch.cat([F.linear(F.silu(taps["emb"]), sd[l[1] + ".emb_layers.1.weight"], sd[l[1] + ".emb_layers.1.bias"])
+                      for b in blocks for l in b["layers"] if l[0] == "res"], dim=1)
+    film = _tap(net, 3, "film")[:, :, 0, 0]
+    assert film.shape == want.shape
+    assert G.report("FiLM table (all emb_layers stacked)", film, want) < 5e-6
+    # classes=None: zero class embedding (adm.py:554-555)
+    unet_ref.unet_forward(cfg, sd, x, t, None, taps=taps)
+    net(x.cuda(), t.cuda(), None)
+    assert G.report("emb, classes=None", _tap(net, 3, "emb")[:, :, 0, 0], taps["emb"]) < 2e-6
