@@ -106,7 +106,7 @@ int ivid_sampler_table(const ivid_sampler_t* s, int which, double* out, int coun
 typedef struct {
   int kind;                 /* 0 = DDPM ancestral (ddpm.py:111-131), 1 = DDIM (ddim.py:48-103) */
   int use_cfg;              /* 1: (1+strength)*eps(c) - strength*eps(null), both halves in ONE batch-2N forward */
-  float strength;
+  float strength;           /* <= 0: ONE forward, eps scaled by (1+strength) when classes are given (classifier_free_guidance.py:40-41) */
   int clip_denoised;
   float eta;
   const int64_t* classes_dev;   /* [N] or NULL */

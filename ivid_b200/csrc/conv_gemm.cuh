@@ -80,6 +80,12 @@ struct ConvGemmCfg {
   static constexpr int EPI_BYTES = 4 * EPI_PER_WARP;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
   static constexpr int THREADS = 256;
+  // kSlab (3x3 tap reuse): activation ring of [18 rows][8 px][64 ch] slabs, weight ring of [BN / kCtas][64] tap tiles
+  static constexpr int SLAB_ROWS = 18;
+  static constexpr int SLAB_A_BYTES = SLAB_ROWS * 8 * BK * 2;                  // 18 KB
+  static constexpr int SLAB_SA = 3, SLAB_SB = 5;
+  static constexpr int SLAB_OPER_BYTES = SLAB_SA * SLAB_A_BYTES + SLAB_SB * B_BYTES;
+  static constexpr int SMEM_BYTES_SLAB = SLAB_OPER_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;
 };
 
 // kMc (cluster multicast, low-resolution levels): a cluster of mc_m x mc_n CTAs computes mc_m pixel tiles x mc_n column blocks.
@@ -89,12 +95,21 @@ struct ConvGemmCfg {
 // bounds the 8x8 level (M = 2048 pixels: every CTA used to stream its own operands, 9 TB/s of L2 reads at 590 TFLOP/s).
 // A stage may be refilled once every CTA that RECEIVES this CTA's slices has consumed it: the MMA commits arrive (multicast) on
 // the empty barriers of the whole row and column, which therefore count mc_n + mc_m - 1 arrivals.
-template <int BN, int kCtas = 1, bool kMc = false>
+//
+// kSlab (3x3 tap reuse, CTA pairs): the pixel tile is 8 wide x 16 high.  Instead of nine tap-shifted 128-pixel boxes per 64-channel
+// chunk, the producer loads THREE [18 rows][8 px] slabs (one per horizontal shift dx, rows y0-1 .. y0+16, zero-filled outside the
+// image) and the three vertical taps of a slab are the same shared-memory bytes read through descriptors that start one slab
+// row (1024 B = one 8-row swizzle atom) apart.  L2 -> shared-memory activation traffic per chunk: 3 x 18 KB instead of 9 x 16 KB;
+// with the nine 16 KB weight tiles (own ring) the operand traffic per FLOP drops by 1.45x.  maps.a_mc[] hold the slab boxes.
+template <int BN, int kCtas = 1, bool kMc = false, bool kSlab = false>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, kCtas>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(!kMc || kCtas == 1, "multicast mode uses single-CTA MMAs");
+  static_assert(!kSlab || (kCtas == 2 && !kMc), "slab mode is built for CTA pairs");
+  constexpr int NA = kSlab ? Cfg::SLAB_SA : STAGES;        // activation (or unified) ring depth
+  constexpr int NB = kSlab ? Cfg::SLAB_SB : 0;             // weight ring depth (slab mode only)
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int mc_rank = kMc ? static_cast<int>(cluster_ctarank()) : 0;
   const int mc_rn = kMc ? mc_rank % p.mc_n : 0, mc_rm = kMc ? mc_rank / p.mc_n : 0;
@@ -105,11 +120,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;            // 1024-aligned (TMA 128B swizzle)
+  uint8_t* stage_smem = smem + (kSlab ? Cfg::SLAB_OPER_BYTES : STAGES * Cfg::STAGE_BYTES);     // 1024-aligned (TMA 128B swizzle)
   uint8_t* bar_area = stage_smem + Cfg::EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NA;
+  uint64_t* bfull_bar = empty_bar + NA;
+  uint64_t* bempty_bar = bfull_bar + NB;
+  uint64_t* tmem_full = bempty_bar + NB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;                               // [4 warps][2 buffers]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
@@ -123,9 +140,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     tma_prefetch_desc(&maps.b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NA; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kMc ? static_cast<uint32_t>(p.mc_n + p.mc_m - 1) : 1u);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&bfull_bar[s], 1);
+      mbar_init(&bempty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -174,7 +195,120 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1] + p.seg_chunks[2] * p.seg_taps[2];
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-  if (warp == 0 && lane == 0) {
+  if (kSlab && warp == 0 && lane == 0) {
+    // ===================================== TMA producer, slab mode =====================================
+    if constexpr (kSlab) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t afull0 = mapa_cluster(smem_u32(&full_bar[0]), 0), bfull0 = mapa_cluster(smem_u32(&bfull_bar[0]), 0);
+      uint8_t* b_ring = smem + Cfg::SLAB_SA * Cfg::SLAB_A_BYTES;
+      for (int w = w_first; w < w_limit; w += w_stride) {
+        int mtp, colbase, ncols;
+        decode(w, mtp, colbase, ncols);
+        const int mt = mtp * 2 + static_cast<int>(cta_rank);
+        const int tn = mt / tiles_per_img;
+        const int rem = mt - tn * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int tw = rem - th * p.tiles_w;
+        const int n0 = tn * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
+        const bool full = ncols == BN;
+        const CUtensorMap* mapB = full ? &maps.b : &maps.bh;
+        const uint32_t b_bytes = full ? Cfg::B_BYTES : Cfg::B_BYTES / 2;
+        const int bcol = colbase + static_cast<int>(cta_rank) * (ncols / 2);
+        int seg_base = 0;
+        auto load_b = [&](int kcol) {
+          mbar_wait(&bempty_bar[sb], pb ^ 1);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bfull_bar[sb], 2 * b_bytes);
+          tma_load_2d_2sm(mapB, bfull0 + sb * 8, b_ring + sb * Cfg::B_BYTES, kcol, bcol);
+          if (++sb == NB) { sb = 0; pb ^= 1; }
+        };
+#pragma unroll 1
+        for (int seg = 0; seg < 3; ++seg) {
+          const int taps = p.seg_taps[seg];
+          const int chunks = p.seg_chunks[seg];
+          if (chunks == 0) continue;
+#pragma unroll 1
+          for (int ch = 0; ch < chunks; ++ch) {
+            if (taps == 9) {
+#pragma unroll 1
+              for (int dx = 0; dx < 3; ++dx) {
+                mbar_wait(&empty_bar[sa], pa ^ 1);
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB_A_BYTES);
+                tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * Cfg::SLAB_A_BYTES, ch * 64, w0 + dx - 1, h0 - 1, n0);
+                if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+                for (int dy = 0; dy < 3; ++dy) load_b(seg_base + ((dy * 3 + dx) * chunks + ch) * 64);
+              }
+            } else {
+              mbar_wait(&empty_bar[sa], pa ^ 1);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::A_BYTES);
+              tma_load_4d_2sm(&maps.a[seg], afull0 + sa * 8, smem + sa * Cfg::SLAB_A_BYTES, ch * 64, w0, h0, n0);
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+              load_b(seg_base + ch * 64);
+            }
+          }
+          seg_base += taps * chunks * 64;
+        }
+      }
+    }
+  } else if (kSlab && warp == 1 && lane == 0 && cta_rank == 0) {
+    // ===================================== MMA issuer, slab mode =====================================
+    if constexpr (kSlab) {
+      constexpr uint32_t idesc_full = make_idesc_f16(256, BN, false, false, false);
+      constexpr uint32_t idesc_half = make_idesc_f16(256, BN / 2, false, false, false);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t b_ring = smem_u32(smem + Cfg::SLAB_SA * Cfg::SLAB_A_BYTES);
+      for (int w = w_first; w < w_limit; w += w_stride) {
+        const uint32_t idesc = (w >= p.full_items) ? idesc_half : idesc_full;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        uint32_t accum = 0;
+        auto tap = [&](uint32_t a_addr) {          // one weight tile against the activation rows starting at a_addr
+          mbar_wait(&bfull_bar[sb], pb);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(a_addr, 1024, 16);
+          const uint64_t db = make_smem_desc_sw128(b_ring + sb * Cfg::B_BYTES, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+            accum = 1u;
+          }
+          tc_commit_2sm(&bempty_bar[sb]);
+          if (++sb == NB) { sb = 0; pb ^= 1; }
+        };
+#pragma unroll 1
+        for (int seg = 0; seg < 3; ++seg) {
+          const int taps = p.seg_taps[seg];
+          const int chunks = p.seg_chunks[seg];
+          if (chunks == 0) continue;
+#pragma unroll 1
+          for (int ch = 0; ch < chunks; ++ch) {
+            const int nslab = taps == 9 ? 3 : 1;
+#pragma unroll 1
+            for (int dx = 0; dx < nslab; ++dx) {
+              mbar_wait(&full_bar[sa], pa);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smem + sa * Cfg::SLAB_A_BYTES);
+              if (taps == 9) {
+#pragma unroll 1
+                for (int dy = 0; dy < 3; ++dy) tap(a_addr + dy * 1024);      // slab row dy = image row y0 - 1 + dy
+              } else {
+                tap(a_addr);
+              }
+              tc_commit_2sm(&empty_bar[sa]);
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+        tc_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (!kSlab && warp == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
     int stage = 0;
     uint32_t phase = 0;
@@ -233,7 +367,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+  } else if (!kSlab && warp == 1 && lane == 0 && cta_rank == 0) {
     // ===================================== MMA issuer (leader CTA only in 2-CTA mode) =====================================
     constexpr uint32_t idesc_full = make_idesc_f16(128 * kCtas, BN, false, false, false);
     constexpr uint32_t idesc_half = make_idesc_f16(128 * kCtas, BN >= 32 ? BN / 2 : BN, false, false, false);

@@ -22,6 +22,7 @@ struct ConvLaunch {
   int grid;
   int ctas = 1;          // 2 = CTA-pair kernel (cluster of 2, cta_group::2 MMA)
   int mc = 0;            // > 0: cluster-multicast kernel, cluster size mc = mc_n * mc_m
+  int slab = 0;          // 1: 3x3 tap-reuse kernel (8 x 16 pixel tiles, [18][8] activation slabs), CTA pairs only
 };
 
 int conv_pad_cout(int cout) {
@@ -121,6 +122,13 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     l->ctas = (pair_ok && l->BN == 256 && m_tiles % 2 == 0 && m_tiles >= 2) ? 2 : 1;
     if (l->BN == 256 && l->ctas == 1 && (pair_ok || d.out16 != nullptr)) l->BN = 128;
+    // 3x3 tap reuse (conv_gemm_kernel<.., kSlab>): 8 x 16 pixel tiles; not with the upsampled residual (16-wide boxes)
+    const int slab_mode = getenv("IVID_SLAB") ? atoi(getenv("IVID_SLAB")) : 0;      // read per plan build (tests switch it)
+    if (slab_mode && l->ctas == 2 && d.taps0 == 9 && d.H >= 16 && d.W >= 16 && !d.residual_up) {
+      l->slab = 1;
+      p.TW = 8; p.TH = 16; p.TN = 1;
+      p.tiles_w = d.W / p.TW; p.tiles_h = d.H / p.TH; p.tiles_n = d.N;
+    }
   }
   p.n_blocks = d.cout_pad / l->BN;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
@@ -198,6 +206,11 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     }
   }
   if (l->mc == 0) { M.a_mc[0] = M.a[0]; M.a_mc[1] = M.a[0]; M.a_mc[2] = M.a[0]; M.b_mc = M.b; }
+  if (l->slab) {
+    M.a_mc[0] = make_act_map(d.act0, d.N, d.H, d.W, d.C0, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+    if (d.C1 > 0 && d.taps1 == 9) M.a_mc[1] = make_act_map(d.act1, d.N, d.H, d.W, d.C1, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+    if (d.C2 > 0 && d.taps2 == 9) M.a_mc[2] = make_act_map(d.act2, d.N, d.H, d.W, d.C2, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+  }
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
   M.out = M.a[0]; M.res = M.a[0]; M.out16 = M.a[0];
   p.out16 = 0;
@@ -260,18 +273,21 @@ static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
   static std::once_flag once;
   std::call_once(once, [] {
     IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    IVID_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<256, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES_SLAB));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(l->grid);
   cfg.blockDim = dim3(Cfg::THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = l->slab ? Cfg::SMEM_BYTES_SLAB : Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->maps, l->p));
+  if (l->slab) IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2, false, true>, l->maps, l->p));
+  else IVID_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, 2>, l->maps, l->p));
 }
 static void run_conv_mc(const ConvLaunch* l, cudaStream_t s) {
   using Cfg = ConvGemmCfg<128, 1>;

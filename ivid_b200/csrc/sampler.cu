@@ -172,7 +172,9 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   const bool has_classes = a.classes_dev != nullptr;
   const bool cfg_two = a.use_cfg && has_classes && a.strength > 0.0f;
   // inpaint_cfg.py:77-78 / sr_cfg.py:53-54: classes None -> single null-class forward, no (1+s) scaling
-  const bool scale_only = a.use_cfg && has_classes && !(a.strength > 0.0f);
+  // strength < 0: (1 + strength) * eps of ONE forward (classifier_free_guidance.py:40-41); the conditional frameworks skip even
+  // that when classes is None
+  const bool scale_only = a.use_cfg && a.strength < 0.0f && (has_classes || a.cond.kind == 0);
   const int Nf = cfg_two ? 2 * N : N;
   IVID_CHECK_CUDA(cudaSetDevice(unet.device()));      // before any allocation: a direct C-ABI caller may be on another device
   ensure_device(Nf, static_cast<size_t>(Nf) * C * HW);
@@ -207,7 +209,8 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   p.t_index = &reinterpret_cast<StepState*>(d_state_)->t_index;
   p.t_prev = &reinterpret_cast<StepState*>(d_state_)->t_prev;
   p.N = N; p.C = C; p.HW = HW;
-  p.cfg = cfg_two ? 1 : 0;
+  // strength <= 0 with classes: (1 + strength) * eps_c without the null-class forward (classifier_free_guidance.py:40-41)
+  p.cfg = cfg_two ? 1 : (scale_only ? 2 : 0);
   p.strength = a.strength;
   p.clip = a.clip_denoised; p.eta = a.eta; p.seed = a.seed; p.stream = 0;
   p.stream_dev = &reinterpret_cast<StepState*>(d_state_)->stream;
@@ -221,10 +224,6 @@ void Sampler::step(Unet& unet, const float* x_t, float* x_prev, float* pred_x0, 
   IVID_REQUIRE(g.depth == nullptr || g.depth_mask != nullptr, "replace_depth needs its mask");
   IVID_REQUIRE(g.convex == nullptr || g.depth != nullptr, "constrain_depth is applied inside replace_depth (ddim.py:90-95)");
   IVID_REQUIRE(!ddim ? (g.rgb == nullptr && g.depth == nullptr) : true, "replace/constrain guidance is DDIM-only");
-  // strength <= 0: the reference returns (1 + strength) * eps_c without the null-class forward
-  // (classifier_free_guidance.py:40-41); only strength == 0 (plain eps_c) is on this path.
-  if (scale_only && a.strength != 0.0f)
-    throw Error(kErrNotImplemented, "classifier-free guidance with strength < 0 is not supported");
 
   unet.set_cond_stream_dev(cond.kind != 0 && cond.noise_dev == nullptr ? &reinterpret_cast<StepState*>(d_state_)->stream : nullptr);
   // Fused route: the output head's last kernel IS the step (head_step_kernel): eps never reaches HBM and the update is the last

@@ -70,7 +70,7 @@ struct StepParams {
   const int* t_index;          // device scalar: table row for the model timestep (t for DDPM, t-1 for DDIM)
   const int* t_prev;           // DDIM: device scalar t_prev (acp_prev row); DDPM: unused
   int N, C, HW;
-  int cfg;                     // 1: eps = (1+s)*eps_c - s*eps_u
+  int cfg;                     // 1: eps = (1+s)*eps_c - s*eps_u;  2: eps = (1+s)*eps_c (strength <= 0: no null-class forward)
   float strength;
   int clip;
   float eta;
@@ -89,6 +89,7 @@ __device__ __forceinline__ float cfg_mix(float ec, float eu, float strength) {
 __device__ __forceinline__ float mix_eps(const StepParams& p, size_t i, size_t total) {
   const float ec = p.eps[i];
   if (!p.cfg) return ec;
+  if (p.cfg == 2) return __fmul_rn(__fadd_rn(1.0f, p.strength), ec);
   return cfg_mix(ec, p.eps[total + i], p.strength);
 }
 
@@ -235,11 +236,14 @@ __global__ void __launch_bounds__(256) head_step_kernel(const HeadStepParams h) 
     for (int j = 0; j < 4; ++j) {
       float ec[4];
       head_eps4(h, n, y, xg * 4 + j, ec);
-      if (p.cfg) {
+      if (p.cfg == 1) {
         float eu[4];
         head_eps4(h, n + p.N, y, xg * 4 + j, eu);
 #pragma unroll
         for (int c = 0; c < 4; ++c) ec[c] = cfg_mix(ec[c], eu[c], p.strength);
+      } else if (p.cfg == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ec[c] = __fmul_rn(__fadd_rn(1.0f, p.strength), ec[c]);
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) e[j][c] = ec[c];

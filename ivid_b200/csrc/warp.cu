@@ -206,6 +206,7 @@ __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S,
 // frustum ring and faces stretched across depth discontinuities) are broadcast to the warp and scanned by all 32 lanes.
 // `stash` = this warp's 32 rows of a shared-memory table: a lane parks its big triangle there and the warp reads the leader's row
 // (a broadcast load) instead of keeping two set-up triangles in registers and shuffling 36 words per triangle.
+template <bool kSmemTri>
 __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* vis, int lane, int simple, uint32_t (*stash)[kRTriWords]) {
   constexpr int kSmall = 48;
   const int w = r.valid ? (r.px1 - r.px0 + 1) : 0, h = r.valid ? (r.py1 - r.py0 + 1) : 0;
@@ -225,10 +226,15 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
   while (mask) {
     const int leader = __ffs(mask) - 1;
     mask &= mask - 1;
-    RTri b;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&b);
+    // the leader's record is read in place (warp-uniform addresses: broadcast loads), which keeps the kernel at 96 registers
+    // (5 blocks per SM) instead of 122 with a register copy
+    RTri breg;
+    if (!kSmemTri) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&breg);
 #pragma unroll
-    for (int i = 0; i < kRTriWords; ++i) dst[i] = stash[leader][i];
+      for (int i = 0; i < kRTriWords; ++i) dst[i] = stash[leader][i];
+    }
+    const RTri& b = kSmemTri ? *reinterpret_cast<const RTri*>(stash[leader]) : breg;
     // 8x8-pixel tiles of the bounding box; a tile is skipped when one edge function is negative at its most-inside corner
     // (exact integer test, so the surviving pixels are decided by the same arithmetic as the small path).  The tiles are
     // TESTED 32 at a time (one tile per lane: the frustum-ring slivers have bounding boxes of thousands of tiles of which a
@@ -269,15 +275,18 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
   __syncwarp();      // the stash rows are reused by the next sub-triangle of this warp
 }
 
-__global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
+template <bool kSmemTri, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) raster_kernel(const RasterParams p) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int view = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31;
-  __shared__ uint32_t s_stash[128][kRTriWords];
+  __shared__ __align__(16) uint32_t s_stash[128][kRTriWords];
+  __shared__ __align__(16) uint32_t s_second[128][kRTriWords];      // the rare second sub-triangle of a near-clipped face waits here
   uint32_t (*stash)[kRTriWords] = s_stash + (threadIdx.x & ~31);
   unsigned long long* vis = p.vis + (static_cast<size_t>(b) * p.nviews + view) * p.S * p.S;
-  RTri t0, t1;
-  t0.valid = 0; t1.valid = 0;
+  RTri t;
+  t.valid = 0;
+  bool second = false;
   if (f < p.F) {
     // faces are visited in a permuted order (7919 is coprime to the face count of any (n+1)^2*2 grid used here) so that
     // the runs of large triangles (frustum ring rows) spread over all warps; primitive ids stay the face indices
@@ -288,14 +297,36 @@ __global__ void __launch_bounds__(128) raster_kernel(const RasterParams p) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) load_vertex(vr.verts, vr.faces[fi * 3 + k], mvp, in[k]);
     const int n = clip_near(in, poly);
-    if (n >= 3) rtri_make(poly, p.S, static_cast<uint32_t>(fi) * 2u, t0);
     if (n == 4) {
       WVtx q[3] = {poly[0], poly[2], poly[3]};
-      rtri_make(q, p.S, static_cast<uint32_t>(fi) * 2u + 1u, t1);
+      rtri_make(q, p.S, static_cast<uint32_t>(fi) * 2u + 1u, t);
+      if (t.valid) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&t);
+#pragma unroll
+        for (int i = 0; i < kRTriWords; ++i) s_second[threadIdx.x][i] = src[i];
+        second = true;
+        t.valid = 0;
+      }
     }
+    if (n >= 3) rtri_make(poly, p.S, static_cast<uint32_t>(fi) * 2u, t);
   }
-  rtri_raster(t0, p.S, vis, lane, p.simple, stash);
-  if (__any_sync(0xffffffffu, t1.valid)) rtri_raster(t1, p.S, vis, lane, p.simple, stash);
+  rtri_raster<kSmemTri>(t, p.S, vis, lane, p.simple, stash);
+  if (__any_sync(0xffffffffu, second)) {      // atomicMin commutes: the order of the two sub-triangles is irrelevant
+    t.valid = 0;
+    if (second) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+      for (int i = 0; i < kRTriWords; ++i) dst[i] = s_second[threadIdx.x][i];
+    }
+    rtri_raster<kSmemTri>(t, p.S, vis, lane, p.simple, stash);
+  }
+}
+
+// IVID_RASTER_REGTRI=1 selects the variant that copies a big triangle into registers (122 registers, 4 blocks per SM): A/B only.
+static void launch_raster(dim3 grid, const RasterParams& rp, cudaStream_t st) {
+  static const bool regtri = [] { const char* e = std::getenv("IVID_RASTER_REGTRI"); return e != nullptr && e[0] == '1'; }();
+  if (regtri) raster_kernel<false, 4><<<grid, 128, 0, st>>>(rp);
+  else raster_kernel<true, 5><<<grid, 128, 0, st>>>(rp);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -1032,7 +1063,7 @@ class Warp {
     RasterParams rp;
     rp.views = views_dev_; rp.mvp = mvp_dev_; rp.vis = vis_; rp.nviews = nviews_; rp.F = F_; rp.S = S_; rp.simple = 0;
     dim3 gr((F_ + 127) / 128, nviews_, B_);
-    raster_kernel<<<gr, 128, 0, st>>>(rp);
+    launch_raster(gr, rp, st);
     ResolveParams sp;
     sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = nviews_; sp.S = S_; sp.T = n_;
     sp.nf_f = static_cast<float>(near_ * far_); sp.far_f = static_cast<float>(far_); sp.fn_f = static_cast<float>(far_ - near_);
@@ -1084,7 +1115,7 @@ class Warp {
     RasterParams rp;
     rp.views = views_dev_; rp.mvp = mvp_dev_; rp.vis = vis_; rp.nviews = 1; rp.F = 2 * (m - 1) * (m - 1); rp.S = S_; rp.simple = 1;
     dim3 gr((rp.F + 127) / 128, 1, B_);
-    raster_kernel<<<gr, 128, 0, st>>>(rp);
+    launch_raster(gr, rp, st);
     ResolveParams sp;
     sp.views = views_dev_; sp.mvp = mvp_dev_; sp.vis = vis_; sp.nviews = 1; sp.S = S_; sp.T = n_;
     sp.nf_f = static_cast<float>(near_ * far_); sp.far_f = static_cast<float>(far_); sp.fn_f = static_cast<float>(far_ - near_);

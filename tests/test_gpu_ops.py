@@ -39,17 +39,23 @@ CONV_CASES = [
     (32, 8, 8, 1024, 1024, 3),   # the 8x8 level of the large model at the benchmark batch: 16 clusters of 8
     (6, 16, 16, 128, 384, 1),    # 16x16 tiles (slices along rows), 3 column blocks: 2 x 1 cluster
     (4, 16, 16, 64, 640, 3),     # 5 column blocks (odd): 2 x 1 cluster, weight multicast only
+    # 3x3 tap-reuse kernel (CTA pairs, 8 x 16 pixel tiles)
+    (5, 32, 32, 192, 512, 3),    # odd batch, 3 channel chunks, 80 tiles = 40 pairs x 2 column blocks
+    (13, 16, 16, 128, 768, 3),   # 16x16 images: one tile row per image (slab rows -1 and 16 are zero fill), 3 column blocks
 ]
 
 
-@pytest.fixture(params=["default", "multicast"])
+@pytest.fixture(params=["default", "multicast", "slab"])
 def conv_mode(request, monkeypatch):
-    """Every conv case runs through the default kernels and through the opt-in cluster-multicast kernel (IVID_MC=1 is read when
-    a launch is created; it only takes effect on low-resolution N = 128 layers)."""
+    """Every conv case runs through the default kernels, through the opt-in cluster-multicast kernel (IVID_MC=1 is read when
+    a launch is created; it only takes effect on low-resolution N = 128 layers) and through the 3x3 tap-reuse ("slab") kernel
+    (IVID_SLAB=1, CTA-pair layers with H >= 16)."""
+    monkeypatch.delenv("IVID_MC", raising=False)
+    monkeypatch.delenv("IVID_SLAB", raising=False)
     if request.param == "multicast":
         monkeypatch.setenv("IVID_MC", "1")
-    else:
-        monkeypatch.delenv("IVID_MC", raising=False)
+    elif request.param == "slab":
+        monkeypatch.setenv("IVID_SLAB", "1")
     return request.param
 
 
@@ -57,6 +63,8 @@ def conv_mode(request, monkeypatch):
 def test_conv_matches_torch(N, H, W, Cin, Cout, k, conv_mode):
     if conv_mode == "multicast" and H > 16:
         pytest.skip("multicast mode only changes low-resolution layers")
+    if conv_mode == "slab" and (k != 3 or H < 16 or Cout % 256 != 0):
+        pytest.skip("slab mode only changes 3x3 CTA-pair layers")
     rng = _rng(hash((N, H, W, Cin, Cout, k)) % 2**31)
     x = _t(rng, N, Cin, H, W)
     w = _t(rng, Cout, Cin, k, k, scale=1 / math.sqrt(Cin * k * k))
@@ -89,6 +97,34 @@ def test_conv_skip_segment_residual_and_fp16_out():
     assert G.report("conv3x3 + identity residual", out2.permute(0, 3, 1, 2), ref2) < 2e-5
     out3 = G.conv2d(a.half().permute(0, 2, 3, 1).contiguous().cuda(), w, b, 3, out_fp16=True)
     assert G.report("conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), F.conv2d(a.half().float(), w.half().float(), b, padding=1)) < 5e-4
+
+
+def test_conv_slab_segments_residual_and_fp16_out(monkeypatch):
+    """3x3 tap-reuse kernel with a 1x1 skip segment over a second tensor (mixed 9-tap / 1-tap segments share the rings), a
+    two-segment 3x3 input (virtual concat), the identity residual and the fp16 output; same shapes through the default kernel."""
+    rng = _rng(31)
+    N, H, W, C, Cx = 4, 64, 64, 128, 192
+    Co = 512
+    a = _t(rng, N, C, H, W); x = _t(rng, N, Cx, H, W); res = _t(rng, N, Co, H, W)
+    w = _t(rng, Co, C, 3, 3, scale=1 / math.sqrt(9 * C)); b = _t(rng, Co, scale=0.1)
+    ws = _t(rng, Co, Cx, 1, 1, scale=1 / math.sqrt(Cx)); bs = _t(rng, Co, scale=0.1)
+    base = F.conv2d(a.half().float(), w.half().float(), b, padding=1)
+    skip = F.conv2d(x.half().float(), ws.half().float(), bs)
+    an = a.half().permute(0, 2, 3, 1).contiguous().cuda()
+    xn = x.half().permute(0, 2, 3, 1).contiguous().cuda()
+    rn = res.permute(0, 2, 3, 1).contiguous().cuda()
+    for mode in ("1", None):
+        if mode:
+            monkeypatch.setenv("IVID_SLAB", mode)
+        else:
+            monkeypatch.delenv("IVID_SLAB", raising=False)
+        tag = "slab" if mode else "default"
+        out = G.conv2d(an, w, b, 3, act2=xn, w2=ws, b2=bs)
+        assert G.report(f"{tag}: conv3x3 + 1x1 skip segment", out.permute(0, 3, 1, 2), base + skip) < 2e-5
+        out2 = G.conv2d(an, w, b, 3, residual=rn)
+        assert G.report(f"{tag}: conv3x3 + identity residual", out2.permute(0, 3, 1, 2), base + res) < 2e-5
+        out3 = G.conv2d(an, w, b, 3, out_fp16=True)
+        assert G.report(f"{tag}: conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), base) < 5e-4
 
 
 def test_conv_multicast_residual_stats_paths(monkeypatch):

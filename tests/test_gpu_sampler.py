@@ -166,3 +166,29 @@ def test_fused_head_step_equals_separate_step_kernel(golden):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b.samples), "the step arithmetic is pinned (explicit rn intrinsics): both routes give the same bits"
         assert torch.equal(b.pred_x_t[-1], b.samples)
+
+
+def test_negative_guidance_and_cosine_schedule(golden):
+    """Options the reference accepts although no shipped config sets them: strength <= 0 = (1 + strength) * eps_c from ONE forward
+    (classifier_free_guidance.py:40-41) and beta_schedule="cosine" (frameworks/utils.py:31-35), DDIM and DDPM steps."""
+    cfg = _cfg(golden, "tiny")
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
+    fw = frameworks.ClassifierFreeGuidance(_net(cfg, 1234), timesteps=1000, beta_schedule="cosine")
+    tb = sampler_ref.Tables(sampler_ref.get_betas("cosine", 1000))
+    x_t = torch.from_numpy(golden["step_x_t"]); classes = torch.from_numpy(golden["step_classes"])
+    model = lambda x, tt, c: unet_ref.unet_forward(cfg, sd, x, tt, c)
+    ddim, ddpm = samplers.DdimSampler(fw), samplers.DdpmSampler(fw)
+    for strength in (-0.5, 0.0, 2.0):
+        t = torch.tensor([600, 600]); tp = torch.tensor([580, 580])
+        eps = sampler_ref.cfg_eps(model, x_t, t - 1, classes, strength)
+        ref, _ = sampler_ref.ddim_step(tb, x_t, t, tp, eps, torch.zeros_like(x_t))
+        out = ddim.sample_once(x_t.cuda(), t.cuda(), tp.cuda(), classes.cuda(), strength=strength, noise=torch.zeros_like(x_t).cuda())
+        assert G.report(f"cosine ddim step, guidance {strength}", out.pred_x_prev, ref) < STEP_TOL
+        td = torch.tensor([300, 300])
+        noise = torch.from_numpy(np.random.default_rng(5).standard_normal(x_t.shape).astype(np.float32))
+        eps = sampler_ref.cfg_eps(model, x_t, td, classes, strength)
+        ref, _ = sampler_ref.ddpm_step(tb, x_t, td, eps, noise)
+        out = ddpm.sample_once(x_t.cuda(), td.cuda(), classes.cuda(), strength=strength, noise=noise.cuda())
+        assert G.report(f"cosine ddpm step, guidance {strength}", out.pred_x_prev, ref) < STEP_TOL
+    got = fw.model_inference(x_t.cuda(), torch.tensor([500, 500]).cuda(), classes.cuda(), strength=-0.5)
+    assert G.report("cfg model_inference s=-0.5", got, sampler_ref.cfg_eps(model, x_t, torch.tensor([500, 500]), classes, -0.5)) < 1.15e-3

@@ -55,6 +55,30 @@ def test_framework_and_sampler_tables(golden):
         frameworks.GaussianDiffusion(net, timesteps=10, beta_schedule="bogus")
 
 
+def test_cosine_schedule_tables():
+    """beta_schedule="cosine" (frameworks/utils.py:31-35, betas_for_alpha_bar :40-60) against the unmodified reference's betas
+    (tests/golden/schedule_golden.npz); oracle restatement, host mirror and the C++ sampler's float64 tables."""
+    import os
+    from oracle import sampler_ref
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "schedule_golden.npz"))
+    cfg = dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+               attention_resolutions=[16], channel_mult=[1, 2], num_head_channels=64)
+    net = backbones.AdmUnet2d(**cfg)
+    for name, T in (("cosine", 1000), ("cosine", 50), ("linear", 50)):
+        want = g[f"{name}_{T}"]
+        assert np.array_equal(sampler_ref.get_betas(name, T), want)
+        fw = frameworks.GaussianDiffusion(net, timesteps=T, beta_schedule=name)
+        assert np.array_equal(fw.betas, want)
+        tb = sampler_ref.Tables(want)
+        ddpm = samplers.DdpmSampler(fw)
+        names = ["alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+        for i, n in enumerate(names):
+            assert np.array_equal(getattr(ddpm, n), getattr(tb, n)), (name, T, n)
+            # alphas_cumprod reaches 1e-9 at the end of the cosine schedule: products in a different order differ in the last bits
+            assert np.allclose(ddpm.native_table(i), getattr(tb, n), rtol=1e-12, atol=0), (name, T, n)
+
+
 def test_no_cpu_fallback():
     cfg = dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
                attention_resolutions=[16], channel_mult=[1, 2], num_head_channels=64)
