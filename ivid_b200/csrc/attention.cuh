@@ -258,8 +258,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint64_t* kv_empty = kv_full + ST;     // [ST]
   uint64_t* s_full = kv_empty + ST;      // [2]
   uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + 2;         // [2]: P V_j signals o_full[j & 1]
+  uint64_t* o_done = o_full + 2;         // the last P V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -273,7 +274,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     mbar_init(q_full, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); }      // p_full: one arrive per softmax warp
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1); mbar_init(&o_full[1], 1);
+    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -324,7 +326,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       for (int k = 0; k < KV / 16; ++k)
         mma_f16_ts(tmem_base + Cfg::COL_O, dp + 8 * k, dv + 128 * k, idesc_o, (j | k) != 0);
       tc_commit(&kv_empty[st]);
-      tc_commit(o_full);
+      tc_commit(&o_full[j & 1]);
+      if (j == nkv - 1) tc_commit(o_done);
       // S_{j+2} overwrites the columns P_j lives in: ordered behind P V_j by the in-order MMA pipe
       if (j + 2 < nkv) issue_qk(j + 2);
     }
@@ -373,8 +376,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       l_run = l_run * alpha + lsum;
       m_run = m_new;
       if (j > 0 && rescale) {
-        // correction: rescale the running output in place (P V_{j-1} must have landed; P V_j is not issued before p_full)
-        mbar_wait(o_full, (j - 1) & 1);
+        // correction: rescale the running output in place (P V_{j-1} must have landed; P V_j is not issued before p_full).
+        // One barrier per parity of j: with S double-buffered a warp may be two blocks ahead of the P V pipe (S_j was
+        // computed before P V_{j-2} finished), and a parity wait on a single barrier one phase further back returns at once.
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 64; c += 16) {
@@ -391,7 +396,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
-    mbar_wait(o_full, (nkv - 1) & 1);
+    mbar_wait(o_done, 0);
     tc_fence_after();
     const int t = qt * 128 + row;
     const float inv = 1.0f / l_run;
