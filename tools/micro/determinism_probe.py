@@ -1,7 +1,7 @@
 """Run-to-run determinism of the L forward at batch N, eagerly replayed (IVID_NO_GRAPH=1) or through the CUDA graph, with
 per-block taps to localise the first layer whose output differs between two runs.
 
-    [IVID_NO_GRAPH=1] python tools/micro/determinism_probe.py [N=32] [runs=4] [taps=1]
+    [IVID_NO_GRAPH=1] python tools/micro/determinism_probe.py [N=32] [runs=4] [taps=1] [model=L|Lc|SR|S]
 """
 import ctypes, hashlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,10 +15,12 @@ from oracle import unet_ref   # synthetic weights + block names only
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 runs = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 want_taps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-cfg = bench.MODELS["L"]
+cfg = bench.MODELS[sys.argv[4] if len(sys.argv) > 4 else "L"]
 net = backbones.AdmUnet2d(**cfg); net.load_state_dict(unet_ref.make_synthetic_state_dict(cfg, seed=1234)); net = net.cuda(); net.repack()
 g = torch.Generator().manual_seed(3)
-x = torch.randn(N, 4, 128, 128, generator=g).cuda(); t = torch.full((N,), 500, device="cuda"); c = torch.arange(N, device="cuda") % 1000
+S = cfg["image_size"]
+x = torch.randn(N, cfg["in_channels"], S, S, generator=g).cuda(); t = torch.full((N,), 500, device="cuda")
+c = (torch.arange(N, device="cuda") % 1000) if cfg.get("num_classes") else None
 blocks, _ = unet_ref._topology(cfg)
 names = ["input_blocks.0.0"] + [l[1] for b in blocks for l in b["layers"] if l[0] in ("res", "attn")]
 
