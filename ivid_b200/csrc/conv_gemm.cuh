@@ -44,6 +44,8 @@ struct ConvGemmParams {
   int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
+  int res3;                    // epi_tma == 1 with a residual: THREE residual tiles in flight per epilogue warp (the output staging
+                               // tile is then single-buffered): 48 instead of 32 KB of residual reads in flight per SM
   int mc_n, mc_m;              // cluster-multicast mode (kMc): cluster = mc_m pixel tiles x mc_n column blocks
   int debug;                   // perf attribution only (IVID_CONV_DEBUG): 1 = skip stats atomics, 2 = skip global load/store, 4 = skip smem transpose
 };
@@ -128,8 +130,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   uint64_t* bempty_bar = bfull_bar + NB;
   uint64_t* tmem_full = bempty_bar + NB;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;                               // [4 warps][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint64_t* res_full = tmem_empty + 2;                               // [4 warps][2 or 3 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 12);
   float* stat_smem = reinterpret_cast<float*>(bar_area + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -152,7 +154,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4 * kCtas);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 12; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -417,7 +419,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     // ---- TMA epilogue state (CH == 32, fp32 NHWC): the warp's 32 rows form one box (32 ch, TW, box_h, box_n)
     constexpr int NCH = BN / 32;
     uint8_t* epi_base = stage_smem + quarter * Cfg::EPI_PER_WARP;   // out0 | out1 | res0 | res1 | out16, 4 KB each
-    uint64_t* res_bar = res_full + quarter * 2;
+                                                                    // (res3: out | res0 | res1 | res2 | out16)
+    const uint32_t RD = p.res3 ? 3u : 2u;                           // residual tiles in flight
+    uint64_t* res_bar = res_full + quarter * 3;
+    auto res_tile = [&](uint32_t seq) -> uint8_t* {
+      return p.res3 ? epi_base + 4096 + (seq % 3u) * 4096 : epi_base + 8192 + (seq & 1u) * 4096;
+    };
     const int box_h0 = (p.TW * p.TH >= 32) ? ((quarter * 32) / p.TW) % p.TH : 0;
     const int box_n0 = (quarter * 32) / (p.TW * p.TH);
     const bool tma_res = p.epi_tma == 1 && p.residual != nullptr && !(p.debug & 2);
@@ -439,22 +446,22 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       const int mt2 = mtp2 * kCtas + static_cast<int>(cta_rank);
       const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
-      uint64_t* bar = &res_bar[seq & 1];
+      uint64_t* bar = &res_bar[seq % RD];
       if (p.res_up) {
         // the warp's 16 x 2 output pixels are the 2x2 replicas of 8 x 1 source pixels: a [32 ch][8][1][1] box (1 KB)
         mbar_arrive_expect_tx(bar, 1024);
-        tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, (tw2 * p.TW) >> 1,
+        tma_load_4d(&maps.res, bar, res_tile(seq), colbase2 + k2 * 32, (tw2 * p.TW) >> 1,
                     (th2 * p.TH + box_h0) >> 1, tn2 * p.TN + box_n0);
       } else {
         mbar_arrive_expect_tx(bar, 4096);
-        tma_load_4d(&maps.res, bar, epi_base + 8192 + (seq & 1) * 4096, colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
+        tma_load_4d(&maps.res, bar, res_tile(seq), colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
                     tn2 * p.TN + box_n0);
       }
     };
     if constexpr (CH == 32) {
       if (tma_res) {
-        if (lane == 0) { if (total_seq > 0) issue_res(0); if (total_seq > 1) issue_res(1); }
-        res_issued = total_seq < 2 ? total_seq : 2;
+        if (lane == 0) for (uint32_t i = 0; i < RD && i < total_seq; ++i) issue_res(i);
+        res_issued = total_seq < RD ? total_seq : RD;
       }
     }
     const uint32_t tmem_empty0 = (kCtas == 2) ? mapa_cluster(smem_u32(&tmem_empty[0]), 0) : 0u;
@@ -514,12 +521,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           float4 b4[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) b4[j] = ldg_f4(p.bias + col0 + 4 * j);
-          if (tma_res) mbar_wait(&res_bar[res_cnt & 1], (res_cnt >> 1) & 1);
+          if (tma_res) mbar_wait(&res_bar[res_cnt % RD], (res_cnt / RD) & 1);
           tc_wait_ld();
-          if (lane == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has finished reading its tile
+          if (lane == 0) {      // the store that last used this staging tile (two chunks ago; res3: the previous one) has read it
+            if (p.res3) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
           __syncwarp();
-          float4* ob = reinterpret_cast<float4*>(epi_base + (out_cnt & 1) * 4096);
-          const float4* rb = reinterpret_cast<const float4*>(epi_base + 8192 + (res_cnt & 1) * 4096);
+          float4* ob = reinterpret_cast<float4*>(p.res3 ? epi_base : epi_base + (out_cnt & 1) * 4096);
+          const float4* rb = reinterpret_cast<const float4*>(res_tile(res_cnt));
           // optional fp16 copy of the same values (operand of the next GroupNorm / skip conv): two 32-column chunks fill one
           // [32 px][64 ch] tile; its store is committed BEFORE the odd chunk's fp32 store so that wait_group.read<1> at the
           // top of the next chunk also covers it.

@@ -99,6 +99,8 @@ struct GnApplyParams {
   int groups; double inv_count; float eps;
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
+  int film_add;                         // 1: use_scale_shift_norm=False (adm.py:219-221): y = GN(x + e[n][c]) with e = film[n][film_off + c]
+                                        //    added BEFORE the norm; the group moments of x + e follow from the per-channel ones
   int pix_per_block;
   __half* out_act;                      // fp16 [N][Ho][Wo][C]
   __half* out_lo;                       // optional (same-resolution fp16-source path only): fp16(y - float(fp16(y))), the low half
@@ -154,7 +156,14 @@ __device__ __forceinline__ void gn_prologue(const GnApplyParams& p, float* s_ab,
         pb[i] = p.beta[c];
         if (p.film != nullptr) {
           psc[i] = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c];
-          psh[i] = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + C + c];
+          psh[i] = p.film_add ? 0.f : p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + C + c];
+          if (p.film_add) {
+            // sum(x + e) = S + HW e ; sum((x + e)^2) = Q + 2 e S + HW e^2   (HW = 1 / inv_count)
+            const double e = static_cast<double>(psc[i]), hw = 1.0 / p.inv_count;
+            const double S = st[i].x;
+            st[i].x = S + hw * e;
+            st[i].y = st[i].y + 2.0 * e * S + hw * e * e;
+          }
         }
       }
     }
@@ -175,7 +184,9 @@ __device__ __forceinline__ void gn_prologue(const GnApplyParams& p, float* s_ab,
         const float a0 = rstd * pg[i];
         const float b0 = pb[i] - static_cast<float>(mean) * a0;
         float av = a0, bv = b0;
-        if (p.film != nullptr) {
+        if (p.film != nullptr && p.film_add) {
+          bv = fmaf(psc[i], a0, b0);          // (x + e - mean) * rstd * gamma + beta
+        } else if (p.film != nullptr) {
           const float sc = 1.0f + psc[i];
           av = a0 * sc;
           bv = b0 * sc + psh[i];
@@ -192,8 +203,14 @@ __device__ __forceinline__ void gn_prologue(const GnApplyParams& p, float* s_ab,
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       const double* st = (c < p.C0) ? p.stats0 + (static_cast<size_t>(n) * p.C0 + c) * 2
                                     : p.stats1 + (static_cast<size_t>(n) * p.C1 + (c - p.C0)) * 2;
-      s += st[0];
-      q += st[1];
+      double sc = st[0], qc = st[1];
+      if (p.film != nullptr && p.film_add) {
+        const double e = static_cast<double>(p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c]), hw = 1.0 / p.inv_count;
+        qc = qc + 2.0 * e * sc + hw * e * e;
+        sc = sc + hw * e;
+      }
+      s += sc;
+      q += qc;
     }
     const double cnt_inv = p.inv_count / cpg;
     const double mean = s * cnt_inv;
@@ -208,7 +225,9 @@ __device__ __forceinline__ void gn_prologue(const GnApplyParams& p, float* s_ab,
     const float a0 = s_rstd[g] * p.gamma[c];
     const float b0 = p.beta[c] - s_mean[g] * a0;
     float a = a0, b = b0;
-    if (p.film != nullptr) {
+    if (p.film != nullptr && p.film_add) {
+      b = fmaf(p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c], a0, b0);
+    } else if (p.film != nullptr) {
       const float sc = 1.0f + p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + c];
       const float sh = p.film[static_cast<size_t>(n) * p.film_ld + p.film_off + C + c];
       a = a0 * sc;

@@ -253,6 +253,8 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     M.out = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     p.epi_tma = 2;
   }
+  // deeper residual prefetch (three tiles in flight per epilogue warp, single output staging tile): opt-in A/B
+  p.res3 = (p.epi_tma == 1 && d.residual != nullptr && getenv("IVID_RES3") != nullptr && getenv("IVID_RES3")[0] == '1') ? 1 : 0;
   // fused statistics are produced by the TMA epilogues only
   if (p.stats != nullptr && p.epi_tma == 0) throw Error(kErrInvalidArgument, "conv: fused statistics need a TMA epilogue (Cout % 64 == 0)");
   l->grid = l->ctas == 2 ? 2 * std::min(p.num_items, sm_count() / 2) : std::min(p.num_items, sm_count());
@@ -389,6 +391,7 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   p.silu = d.silu ? (silu_wrapped ? 2 : 1) : 0;
   p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
   p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
+  p.film_add = d.film_add ? 1 : 0;
   p.out_act = reinterpret_cast<__half*>(d.out_act); p.out_raw16 = reinterpret_cast<__half*>(d.out_raw16);
   p.out_raw32 = d.out_raw32;
   p.out_lo = reinterpret_cast<__half*>(d.out_lo);

@@ -56,6 +56,7 @@ struct GnApplyDesc {
   int groups = 32; float eps = 1e-5f;
   const float* gamma = nullptr; const float* beta = nullptr;        // [C0 + C1]
   const float* film = nullptr; int film_ld = 0, film_off = 0;       // optional FiLM table (scale | shift)
+  bool film_add = false;                                            // table holds ONE row per channel, added before the norm
   void* out_act = nullptr; void* out_raw16 = nullptr; float* out_raw32 = nullptr;
   void* out_lo = nullptr;      // optional low half of a two-term fp16 split of the output (fp16-source same-resolution path only)
 };

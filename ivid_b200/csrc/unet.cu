@@ -77,7 +77,6 @@ const ParamSpec& Unet::P(const std::string& name) const {
 // key names ("input_blocks.3.0.in_layers.0.weight", ...) and shapes match torch's registration order.
 void Unet::build_topology() {
   const UnetConfig& c = cfg_;
-  if (!c.use_scale_shift_norm) throw Error(kErrNotImplemented, "use_scale_shift_norm=False is not on the sampling hot path");
   if (!c.resblock_updown) throw Error(kErrNotImplemented, "resblock_updown=False is not on the sampling hot path");
   IVID_REQUIRE(c.model_channels % 64 == 0, "model_channels must be a multiple of 64 (tensor-core K slab)");
   IVID_REQUIRE(c.in_channels <= 16, "in_channels must be <= 16");
@@ -107,8 +106,9 @@ void Unet::build_topology() {
     add_param(pfx + ".in_layers.0.bias", {cin});
     add_param(pfx + ".in_layers.2.weight", {cout, cin, 3, 3});
     add_param(pfx + ".in_layers.2.bias", {cout});
-    add_param(pfx + ".emb_layers.1.weight", {2 * cout, E});
-    add_param(pfx + ".emb_layers.1.bias", {2 * cout});
+    const int ew = c.use_scale_shift_norm ? 2 * cout : cout;          // adm.py:176
+    add_param(pfx + ".emb_layers.1.weight", {ew, E});
+    add_param(pfx + ".emb_layers.1.bias", {ew});
     add_param(pfx + ".out_layers.0.weight", {cout});
     add_param(pfx + ".out_layers.0.bias", {cout});
     add_param(pfx + ".out_layers.3.weight", {cout, cout, 3, 3});
@@ -119,7 +119,7 @@ void Unet::build_topology() {
       add_param(pfx + ".skip_connection.bias", {cout});
     }
     r.film_off = film_total_;
-    film_total_ += 2 * cout;
+    film_total_ += ew;
     res_.push_back(r);
     return static_cast<int>(res_.size()) - 1;
   };
@@ -627,11 +627,12 @@ Plan* Unet::build_plan(int N) {
       pend.gamma = Wf(g.g_off); pend.beta = Wf(g.b_off);
       pend.film = film_off >= 0 ? s_film : nullptr;
       pend.film_ld = film_total_; pend.film_off = std::max(film_off, 0);
+      pend.film_add = film_off >= 0 && !cfg_.use_scale_shift_norm;
     };
     auto add_apply = [&](GnApplyDesc d) {
       if (!create) return;
       d.stats0 = pend.stats0; d.stats1 = pend.stats1; d.groups = pend.groups; d.eps = pend.eps; d.gamma = pend.gamma;
-      d.beta = pend.beta; d.film = pend.film; d.film_ld = pend.film_ld; d.film_off = pend.film_off;
+      d.beta = pend.beta; d.film = pend.film; d.film_ld = pend.film_ld; d.film_off = pend.film_off; d.film_add = pend.film_add;
       {
         const int Ho = d.mode == 1 ? d.H * 2 : (d.mode == 2 ? d.H / 2 : d.H);
         const double in_el = static_cast<double>(d.N) * d.H * d.W * (d.C0 + d.C1);

@@ -112,8 +112,9 @@ def unet_param_shapes(cfg: dict) -> Dict[str, tuple]:
                 out[p + ".in_layers.0.bias"] = (cin,)
                 out[p + ".in_layers.2.weight"] = (cout, cin, 3, 3)
                 out[p + ".in_layers.2.bias"] = (cout,)
-                out[p + ".emb_layers.1.weight"] = (2 * cout, E)
-                out[p + ".emb_layers.1.bias"] = (2 * cout,)
+                ew = 2 * cout if c["use_scale_shift_norm"] else cout         # adm.py:176
+                out[p + ".emb_layers.1.weight"] = (ew, E)
+                out[p + ".emb_layers.1.bias"] = (ew,)
                 out[p + ".out_layers.0.weight"] = (cout,)
                 out[p + ".out_layers.0.bias"] = (cout,)
                 out[p + ".out_layers.3.weight"] = (cout, cout, 3, 3)
@@ -170,7 +171,7 @@ def _group_norm(x, sd, p, groups):
 
 
 def _resblock(x, emb, sd, p, mode, groups, taps: Optional[dict] = None):
-    # ResBlock2d.forward (adm.py:192-222) with use_scale_shift_norm=True
+    # ResBlock2d.forward (adm.py:192-222); use_scale_shift_norm is read off the width of emb_layers (adm.py:176)
     h = F.silu(_group_norm(x, sd, p + ".in_layers.0", groups))
     if mode == "up":       # Upsample2d without conv: nearest x2 on both branches (adm.py:89, 203-207)
         h = F.interpolate(h, scale_factor=2, mode="nearest")
@@ -180,8 +181,11 @@ def _resblock(x, emb, sd, p, mode, groups, taps: Optional[dict] = None):
         x = F.avg_pool2d(x, 2)
     h = F.conv2d(h, sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.2.bias"], padding=1)
     emb_out = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])[:, :, None, None]
-    scale, shift = torch.chunk(emb_out, 2, dim=1)
-    h = _group_norm(h, sd, p + ".out_layers.0", groups) * (1 + scale) + shift
+    if emb_out.shape[1] == 2 * h.shape[1]:          # use_scale_shift_norm (adm.py:214-218)
+        scale, shift = torch.chunk(emb_out, 2, dim=1)
+        h = _group_norm(h, sd, p + ".out_layers.0", groups) * (1 + scale) + shift
+    else:                                           # adm.py:219-221: h = h + emb_out; out_layers(h)
+        h = _group_norm(h + emb_out, sd, p + ".out_layers.0", groups)
     h = F.conv2d(F.silu(h), sd[p + ".out_layers.3.weight"], sd[p + ".out_layers.3.bias"], padding=1)
     if (p + ".skip_connection.weight") in sd:
         x = F.conv2d(x, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])

@@ -127,6 +127,23 @@ def test_conv_slab_segments_residual_and_fp16_out(monkeypatch):
         assert G.report(f"{tag}: conv3x3 fp16 out", out3.float().permute(0, 3, 1, 2), base) < 5e-4
 
 
+@pytest.mark.parametrize("N,H,W,Cin,C", [(2, 64, 64, 64, 768), (4, 64, 64, 128, 512), (2, 16, 16, 128, 128), (1, 128, 128, 64, 256)])
+def test_conv_residual_three_tiles_in_flight(monkeypatch, N, H, W, Cin, C):
+    """IVID_RES3=1: the fp32 epilogue keeps three residual tiles in flight per warp (single output staging tile): CTA pairs with a
+    split tail, plain pairs, single-CTA N = 128 tiles; identical bits to the default epilogue."""
+    rng = _rng(N * 1000 + C)
+    a = _t(rng, N, Cin, H, W); res = _t(rng, N, C, H, W)
+    w = _t(rng, C, Cin, 3, 3, scale=1 / math.sqrt(9 * Cin)); b = _t(rng, C, scale=0.1)
+    an = a.half().permute(0, 2, 3, 1).contiguous().cuda(); rn = res.permute(0, 2, 3, 1).contiguous().cuda()
+    monkeypatch.delenv("IVID_RES3", raising=False)
+    base = G.conv2d(an, w, b, 3, residual=rn).clone()
+    monkeypatch.setenv("IVID_RES3", "1")
+    got = G.conv2d(an, w, b, 3, residual=rn)
+    assert torch.equal(got, base)
+    ref = F.conv2d(a.half().float(), w.half().float(), b, padding=1) + res
+    assert G.report(f"res3: conv3x3 + residual N{N} {H}x{W} {Cin}->{C}", got.permute(0, 3, 1, 2), ref) < 2e-5
+
+
 def test_conv_multicast_residual_stats_paths(monkeypatch):
     """Cluster-multicast kernel through the residual-prefetch epilogue, the fp16-output epilogue and the 1x1 skip segment."""
     monkeypatch.setenv("IVID_MC", "1")

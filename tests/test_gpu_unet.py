@@ -198,3 +198,26 @@ def test_large_model_batch32_deterministic_and_batch_invariant(golden):
     for i in (0, 13, 31):
         one = net(x[i:i + 1].contiguous(), t[i:i + 1], c[i:i + 1])
         assert torch.equal(one, first[i:i + 1]), f"sample {i}: eps depends on the batch"
+
+
+def test_option_without_scale_shift_norm():
+    """use_scale_shift_norm=False (adm.py:219-221): the time/class embedding is ADDED before out_layers' GroupNorm; the native
+    plan derives the moments of h + e from the per-channel statistics the conv epilogue already accumulates and folds e into the
+    affine of the apply kernel.  Against the unmodified reference's eps (options_golden.npz) and the oracle's per-block taps."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options_golden.npz"))
+    cfg = json.loads(bytes(g["noshift_cfg"]).decode())
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=77)
+    net = _load(cfg, sd)
+    x = torch.from_numpy(g["noshift_x"]); t = torch.from_numpy(g["noshift_t"]); c = torch.from_numpy(g["noshift_c"])
+    got = net(x.cuda(), t.cuda(), c.cuda())
+    ref = torch.from_numpy(g["noshift_eps"])
+    r = G.report("eps, use_scale_shift_norm=False", got, ref)
+    print(f"[noshift] eps rel {r:.3e}")
+    assert r < 1.6e-3
+    taps = {}
+    unet_ref.unet_forward(cfg, sd, x, t, c, taps=taps)
+    for name in ("input_blocks.1.0", "middle_block.0", "output_blocks.2.0"):
+        rt = G.rel(_tap(net, 2, name), taps[name])
+        print(f"[noshift] {name} rel {rt:.3e}")
+        assert rt < 1.6e-3

@@ -63,3 +63,17 @@ def test_sampler_oracle_steps(golden):
         assert float((xp - ref).norm() / ref.norm()) < 1e-5
     assert torch.equal(sampler_ref.make_sr_inputs(torch.from_numpy(golden["sr_x"]), torch.from_numpy(golden["sr_y"])),
                        torch.from_numpy(golden["sr_cond_inputs"]))
+
+
+def test_unet_oracle_option_without_scale_shift_norm():
+    """use_scale_shift_norm=False (adm.py:176, 219-221: h = out_layers(h + emb_out)) against the unmodified reference's eps
+    (tests/golden/options_golden.npz, made by tests/golden/make_options_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options_golden.npz"))
+    cfg = json.loads(bytes(g["noshift_cfg"]).decode())
+    assert cfg["use_scale_shift_norm"] is False
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=77)
+    assert sd["input_blocks.1.0.emb_layers.1.weight"].shape[0] == sd["input_blocks.1.0.out_layers.0.weight"].shape[0]
+    y = unet_ref.unet_forward(cfg, sd, torch.from_numpy(g["noshift_x"]), torch.from_numpy(g["noshift_t"]), torch.from_numpy(g["noshift_c"]))
+    ref = torch.from_numpy(g["noshift_eps"])
+    assert float((y - ref).norm() / ref.norm()) < 1e-5
