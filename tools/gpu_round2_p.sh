@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round-2 GPU batch P: 3-deep residual prefetch in the conv epilogue (IVID_RES3) parity + A/B; use_scale_shift_norm=False parity.
+mkdir -p gpurun_out
+TAG=${TAG:-r02p}
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -30 gpurun_out/build.log; }
+timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu -x -k "residual or res3" > gpurun_out/pytest_gpu_${TAG}_ops.log 2>&1; echo "== pytest ops exit $?"; tail -4 gpurun_out/pytest_gpu_${TAG}_ops.log
+timeout 600 python -m pytest tests/test_gpu_unet.py -q -m gpu -x -s -k "without_scale_shift" > gpurun_out/pytest_gpu_${TAG}_noshift.log 2>&1; echo "== pytest noshift exit $?"; grep "noshift\|passed\|failed\|Error" gpurun_out/pytest_gpu_${TAG}_noshift.log | tail -8
+IVID_RES3=1 timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_sampler.py -q -m gpu -x > gpurun_out/pytest_gpu_${TAG}_res3.log 2>&1; echo "== pytest unet+sampler res3 exit $?"; tail -3 gpurun_out/pytest_gpu_${TAG}_res3.log
+for v in "IVID_RES3=0" "IVID_RES3=1" "IVID_RES3=0" "IVID_RES3=1"; do
+  env $v IVID_PROFILE_OPS=1 timeout 600 python bench.py --config 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_c2_${v}.json 2>gpurun_out/bench_${TAG}.err
+  cp gpurun_out/per_op_profile_c2.json gpurun_out/per_op_${TAG}_${v}.json 2>/dev/null
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_${TAG}_c2_${v}.json").read().strip().splitlines()[-1])
+    f=d["roofline"]["families"]
+    print("c2 ${v}: ms/step %.3f"%d["ms_per_step"], {k:(v["launches"], round(v["ms"],3)) for k,v in f.items() if k.startswith("conv") or k.startswith("gn")}, d["clocks"])
+except Exception as e:
+    print("parse failed", e)
+PY
+done
+tail -3 gpurun_out/bench_${TAG}.err
