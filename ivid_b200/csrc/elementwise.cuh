@@ -403,6 +403,71 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyParams p)
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Plain resampling layers (resblock_updown=False: Downsample2d / Upsample2d, reference adm.py:60-117)
+// ----------------------------------------------------------------------------------------------
+// Operand of the stride-2 3x3 convolution of Downsample2d (adm.py:111):  col[n][yo][xo][tap*C + c] = x[n][2yo+dy-1][2xo+dx-1][c]
+// (zero outside the image), tap = dy*3 + dx, so that the packed 3x3 weights ([Cout][tap][C]) apply as a 1x1 GEMM over 9C channels.
+__global__ void __launch_bounds__(256) im2col_s2_h16_kernel(const __half* __restrict__ x, __half* __restrict__ col, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, c8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * 9 * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    const int tap = static_cast<int>((i / c8) % 9);
+    const size_t pix = i / (static_cast<size_t>(c8) * 9);
+    const int xo = static_cast<int>(pix % Wo), yo = static_cast<int>((pix / Wo) % Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+    const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+      v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + yi) * W + xi) * C + cg * 8));
+    *reinterpret_cast<uint4*>(col + (pix * 9 + tap) * C + cg * 8) = v;
+  }
+}
+
+// Upsample2d (adm.py:89): nearest 2x of an fp16 NHWC tensor (the operand of its 3x3 conv)
+__global__ void __launch_bounds__(256) upsample2x_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, int N, int H, int W, int C) {
+  const int Ho = H * 2, Wo = W * 2, c8 = C >> 3;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    const size_t pix = i / c8;
+    const int xo = static_cast<int>(pix % Wo), yo = static_cast<int>((pix / Wo) % Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+    *reinterpret_cast<uint4*>(out + pix * C + cg * 8) =
+        __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + (yo >> 1)) * W + (xo >> 1)) * C + cg * 8));
+  }
+}
+
+// conv_resample=False: AvgPool2d(2) (mode 2, adm.py:113) / nearest 2x (mode 1, adm.py:89) of an fp32 NHWC block output
+// -> fp32 NHWC (+ fp16 copy for the next GroupNorm / skip conv)
+__global__ void __launch_bounds__(256) resample_f32_kernel(const float* __restrict__ x, float* __restrict__ out, __half* __restrict__ out16,
+                                                            int N, int H, int W, int C, int mode) {
+  const int Ho = mode == 1 ? H * 2 : H / 2, Wo = mode == 1 ? W * 2 : W / 2, c4 = C >> 2;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * c4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c4);
+    const size_t pix = i / c4;
+    const int xo = static_cast<int>(pix % Wo), yo = static_cast<int>((pix / Wo) % Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+    float4 v;
+    if (mode == 1) {
+      v = ldg_f4(x + ((static_cast<size_t>(n) * H + (yo >> 1)) * W + (xo >> 1)) * C + cg * 4);
+    } else {
+      const float* b = x + ((static_cast<size_t>(n) * H + 2 * yo) * W + 2 * xo) * C + cg * 4;
+      const float4 a0 = ldg_f4(b), a1 = ldg_f4(b + C), a2 = ldg_f4(b + static_cast<size_t>(W) * C), a3 = ldg_f4(b + static_cast<size_t>(W) * C + C);
+      v = make_float4(((a0.x + a1.x) + (a2.x + a3.x)) * 0.25f, ((a0.y + a1.y) + (a2.y + a3.y)) * 0.25f,
+                      ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f, ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f);
+    }
+    stg_f4(out + pix * C + cg * 4, v);
+    if (out16 != nullptr) {
+      uint2 pk;
+      pk.x = pack_h2(v.x, v.y); pk.y = pack_h2(v.z, v.w);
+      *reinterpret_cast<uint2*>(out16 + pix * C + cg * 4) = pk;
+    }
+  }
+}
+
 // Same-resolution GroupNorm apply over fp16 sources (ResBlock hidden tensor, fp16 copies of block outputs, virtual concat
 // of two) with no raw outputs: the bulk of the element-wise traffic of a forward.  8 work items per trip kept packed
 // (4 registers each) until consumed, so a thread has 128 bytes of reads in flight although an item is only 16 bytes.

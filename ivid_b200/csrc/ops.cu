@@ -429,6 +429,24 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 
+void launch_im2col_s2(const void* x16, void* col, int N, int H, int W, int C, cudaStream_t s) {
+  IVID_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: C % 8, even spatial size");
+  const size_t items = static_cast<size_t>(N) * (H / 2) * (W / 2) * 9 * (C / 8);
+  im2col_s2_h16_kernel<<<ew_grid(items, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(x16), reinterpret_cast<__half*>(col), N, H, W, C);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+void launch_upsample2x_h16(const void* x16, void* out, int N, int H, int W, int C, cudaStream_t s) {
+  IVID_REQUIRE(C % 8 == 0, "upsample2x: C % 8");
+  const size_t items = static_cast<size_t>(N) * H * W * 4 * (C / 8);
+  upsample2x_h16_kernel<<<ew_grid(items, 256), 256, 0, s>>>(reinterpret_cast<const __half*>(x16), reinterpret_cast<__half*>(out), N, H, W, C);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+void launch_resample_f32(const float* x, float* out, void* out16, int N, int H, int W, int C, int mode, cudaStream_t s) {
+  IVID_REQUIRE(C % 4 == 0 && (mode == 1 || (H % 2 == 0 && W % 2 == 0)), "resample_f32: C % 4, even spatial size for pooling");
+  const size_t items = static_cast<size_t>(N) * (mode == 1 ? 4 * H * W : (H / 2) * (W / 2)) * (C / 4);
+  resample_f32_kernel<<<ew_grid(items, 256), 256, 0, s>>>(x, out, reinterpret_cast<__half*>(out16), N, H, W, C, mode);
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
 void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s) {
   IVID_REQUIRE(Cin >= 1 && Cin <= 16, "pack_input: 1..16 input channels (two-term split inside 64 operand channels)");
   pack_input_kernel<<<ew_grid(static_cast<size_t>(N) * HW, 256), 256, 0, s>>>(x, reinterpret_cast<__half*>(out), N, Nx,

@@ -63,6 +63,10 @@ struct GnApplyDesc {
 void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s);
 // eps[n][c][h][w] = bias[c] + sum_tap Y[n][h+dy][w+dx][tap*Co + c]  (output head, see eps_gather_kernel)
 void launch_eps_gather(const float* Y, const float* bias, float* eps, int N, int H, int W, int Co, int ldy, cudaStream_t s);
+// plain Downsample2d / Upsample2d layers (resblock_updown=False): see elementwise.cuh
+void launch_im2col_s2(const void* x16, void* col, int N, int H, int W, int C, cudaStream_t s);
+void launch_upsample2x_h16(const void* x16, void* out, int N, int H, int W, int C, cudaStream_t s);
+void launch_resample_f32(const float* x, float* out, void* out16, int N, int H, int W, int C, int mode, cudaStream_t s);
 void launch_pack_input(const float* x, void* out, int N, int Nx, int Cin, int HW, cudaStream_t s);
 
 struct CondPackDesc {

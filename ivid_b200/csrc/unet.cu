@@ -77,7 +77,6 @@ const ParamSpec& Unet::P(const std::string& name) const {
 // key names ("input_blocks.3.0.in_layers.0.weight", ...) and shapes match torch's registration order.
 void Unet::build_topology() {
   const UnetConfig& c = cfg_;
-  if (!c.resblock_updown) throw Error(kErrNotImplemented, "resblock_updown=False is not on the sampling hot path");
   IVID_REQUIRE(c.model_channels % 64 == 0, "model_channels must be a multiple of 64 (tensor-core K slab)");
   IVID_REQUIRE(c.in_channels <= 16, "in_channels must be <= 16");
   IVID_REQUIRE(c.num_groups >= 1 && c.num_groups <= 64, "num_groups must be in [1,64]");
@@ -136,6 +135,18 @@ void Unet::build_topology() {
     attn_.push_back(a);
     return static_cast<int>(attn_.size()) - 1;
   };
+  auto add_resample = [&](const std::string& pfx, int ch, int mode) {
+    ResampleDef r;
+    r.pfx = pfx; r.C = ch; r.mode = mode; r.conv = c.conv_resample;
+    IVID_REQUIRE(ch % 64 == 0, "channel counts must be multiples of 64");
+    if (r.conv) {
+      const std::string sub = mode == 2 ? ".op" : ".conv";      // Downsample2d.op (adm.py:111) / Upsample2d.conv (adm.py:81)
+      add_param(pfx + sub + ".weight", {ch, ch, 3, 3});
+      add_param(pfx + sub + ".bias", {ch});
+    }
+    resample_.push_back(r);
+    return static_cast<int>(resample_.size()) - 1;
+  };
   auto in_attn = [&](int ds) {
     return std::find(c.attention_resolutions.begin(), c.attention_resolutions.end(), ds) != c.attention_resolutions.end();
   };
@@ -170,7 +181,8 @@ void Unet::build_topology() {
     if (level != levels - 1) {
       BlockDef b;
       b.is_input = true;
-      b.layers.push_back({1, add_res("input_blocks." + std::to_string(ib) + ".0", ch, ch, 2)});
+      if (c.resblock_updown) b.layers.push_back({1, add_res("input_blocks." + std::to_string(ib) + ".0", ch, ch, 2)});
+      else b.layers.push_back({3, add_resample("input_blocks." + std::to_string(ib) + ".0", ch, 2)});      // adm.py:409-412
       blocks_.push_back(b);
       input_block_chs.push_back(ch);
       ++ib;
@@ -198,7 +210,8 @@ void Unet::build_topology() {
       ch = outc;
       if (in_attn(ds)) b.layers.push_back({2, add_attn(pfx + "." + std::to_string(li++), ch)});
       if (level != 0 && i == c.num_res_blocks) {
-        b.layers.push_back({1, add_res(pfx + "." + std::to_string(li++), ch, ch, 1)});
+        if (c.resblock_updown) b.layers.push_back({1, add_res(pfx + "." + std::to_string(li++), ch, ch, 1)});
+        else b.layers.push_back({3, add_resample(pfx + "." + std::to_string(li++), ch, 1)});               // adm.py:475-478
         ds *= 2;
       }
       blocks_.push_back(b);
@@ -356,6 +369,11 @@ void Unet::finalize(int device) {
   in_conv_ = pack_conv("input_blocks.0.0.weight", "input_blocks.0.0.bias", in_ch_stem_, cfg_.in_channels, 64, 3, "", "", 0);
   IVID_REQUIRE(3 * cfg_.in_channels <= 64, "in_channels must be <= 21 (two-term input split inside 64 operand channels)");
   pack_stem_rows(ab.at<__half>(in_conv_.w_off), in_conv_.K, P("input_blocks.0.0.weight").host.data(), in_ch_stem_, cfg_.in_channels, 64);
+  for (auto& r : resample_)
+    if (r.conv) {
+      const std::string sub = r.mode == 2 ? ".op" : ".conv";
+      r.w = pack_conv(r.pfx + sub + ".weight", r.pfx + sub + ".bias", r.C, r.C, r.C, 3, "", "", 0);
+    }
   for (auto& r : res_) {
     r.gn1 = pack_gn(r.pfx + ".in_layers.0", r.cin);
     r.conv1 = pack_conv(r.pfx + ".in_layers.2.weight", r.pfx + ".in_layers.2.bias", r.cout, r.cin, r.cin, 3, "", "", 0);
@@ -493,7 +511,7 @@ Plan* Unet::build_plan(int N) {
   auto Wf = [&](size_t off) { return reinterpret_cast<const float*>(arena_ + off); };
 
   // ---- scratch maxima (walk the topology once for sizes) ----
-  size_t max_act16 = 0, max_raw16 = 0, max_f32 = 0, max_c = 0, max_qkv = 0;
+  size_t max_act16 = 0, max_raw16 = 0, max_f32 = 0, max_c = 0, max_qkv = 0, max_col = 0;
   {
     int res = S;
     auto upd_res = [&](const ResBlockDef& r) {
@@ -507,7 +525,11 @@ Plan* Unet::build_plan(int N) {
     for (const auto& b : blocks_)
       for (const auto& l : b.layers) {
         if (l.kind == 1) upd_res(res_[l.idx]);
-        else {
+        else if (l.kind == 3) {
+          const auto& r = resample_[l.idx];
+          if (r.mode == 2) { max_col = std::max(max_col, static_cast<size_t>(N) * (res / 2) * (res / 2) * 9 * r.C); res /= 2; }
+          else { max_act16 = std::max(max_act16, static_cast<size_t>(N) * (res * 2) * (res * 2) * r.C); res *= 2; }
+        } else {
           const auto& a = attn_[l.idx];
           max_act16 = std::max(max_act16, static_cast<size_t>(N) * res * res * a.C);
           max_qkv = std::max(max_qkv, static_cast<size_t>(N) * res * res * 3 * a.C);
@@ -536,6 +558,8 @@ Plan* Unet::build_plan(int N) {
             const auto& r = res_[l.idx];
             stats_cap += 2 * (static_cast<size_t>(N) * r.cout * 16 + 1024);
             res = r.mode == 1 ? res * 2 : (r.mode == 2 ? res / 2 : res);
+          } else if (l.kind == 3) {
+            stats_cap += static_cast<size_t>(N) * resample_[l.idx].C * 16 + 1024;
           } else {
             stats_cap += static_cast<size_t>(N) * attn_[l.idx].C * 16 + 1024;
           }
@@ -567,6 +591,7 @@ Plan* Unet::build_plan(int N) {
     float* s_h = static_cast<float*>(bump.take(max_f32 * 4));
     void* s_ab = bump.take(static_cast<size_t>(N) * max_c * 2 * 8);      // float2 per (n, c); 2x slack for concat
     void* s_qkv = bump.take(std::max<size_t>(max_qkv, 1) * 2);
+    void* s_col = bump.take(std::max<size_t>(max_col, 1) * 2);           // im2col operand of the stride-2 Downsample2d conv
     float* s_pe = static_cast<float*>(bump.take(static_cast<size_t>(N) * cfg_.model_channels * 4));
     float* s_e1 = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
     float* s_emb = static_cast<float*>(bump.take(static_cast<size_t>(N) * embed_dim_ * 4));
@@ -799,6 +824,50 @@ Plan* Unet::build_plan(int N) {
       return out;
     };
 
+    // plain Downsample2d / Upsample2d (resblock_updown=False): the raw block output is the conv operand (no norm in between)
+    auto run_resample = [&](const ResampleDef& r, const Act& x) -> Act {
+      IVID_REQUIRE(x.C == r.C, "internal: resampling layer width mismatch at " + r.pfx);
+      const int Ho = r.mode == 1 ? x.H * 2 : x.H / 2, Wo = r.mode == 1 ? x.W * 2 : x.W / 2;
+      Act out = new_act(r.C, Ho, Wo);
+      alloc32(out);
+      if (r.conv) {
+        IVID_REQUIRE(x.d16 != nullptr, "internal: resampling conv needs the fp16 copy of its input");
+        const void* x16 = x.d16;
+        const int H = x.H, Wd = x.W, C = r.C;
+        ConvDesc d;
+        if (r.mode == 2) {
+          if (create) {
+            pl->ops.tag("resample", 0, static_cast<double>(N) * Ho * Wo * 9 * C * 4, "im2col s2 " + std::to_string(H) + "x" + std::to_string(Wd) + " C" + std::to_string(C));
+            pl->ops.push_back([=](cudaStream_t s) { launch_im2col_s2(x16, s_col, N, H, Wd, C, s); });
+          }
+          d.act0 = s_col; d.C0 = 9 * C; d.taps0 = 1;
+        } else {
+          if (create) {
+            pl->ops.tag("resample", 0, static_cast<double>(N) * Ho * Wo * C * 2.5, "nearest 2x " + std::to_string(H) + "x" + std::to_string(Wd) + " C" + std::to_string(C));
+            pl->ops.push_back([=](cudaStream_t s) { launch_upsample2x_h16(x16, s_a1, N, H, Wd, C, s); });
+          }
+          d.act0 = s_a1; d.C0 = C; d.taps0 = 9;
+        }
+        d.weight = W8(r.w.w_off); d.cout_pad = r.w.cout_pad; d.cout = C; d.bias = Wf(r.w.b_off);
+        d.out = out.data; d.out16 = out.d16; d.out_mode = 0; d.ldc = C; d.N = N; d.H = Ho; d.W = Wo;
+        add_conv(d, &out, 9.0 * C);
+        add_stats(out);
+      } else {
+        const float* src = use32(x);
+        if (create) {
+          float* dst = out.data; void* dst16 = out.d16;
+          const int H = x.H, Wd = x.W, C = r.C, mode = r.mode;
+          pl->ops.tag("resample", 0, static_cast<double>(N) * (H * Wd + Ho * Wo * 1.5) * C * 4, (mode == 1 ? "nearest 2x f32 " : "avgpool f32 ") + std::to_string(H) + "x" + std::to_string(Wd));
+          pl->ops.push_back([=](cudaStream_t s) { launch_resample_f32(src, dst, dst16, N, H, Wd, C, mode, s); });
+          double* st = stats_ptr(out);
+          pl->ops.tag("gn_stats", 0, static_cast<double>(N) * Ho * Wo * C * 4);
+          pl->ops.push_back([=](cudaStream_t s) { launch_gn_stats(dst, st, N, Ho * Wo, C, s); });
+        }
+      }
+      if (create) pl->taps.push_back({r.pfx, out.data, out.d16, out.C, out.H, out.W});
+      return out;
+    };
+
     for (size_t bi = 1; bi < blocks_.size(); ++bi) {
       const BlockDef& b = blocks_[bi];
       bool first = true;
@@ -811,6 +880,8 @@ Plan* Unet::build_plan(int N) {
           } else {
             cur = run_res(res_[l.idx], cur, nullptr);
           }
+        } else if (l.kind == 3) {
+          cur = run_resample(resample_[l.idx], cur);
         } else {
           cur = run_attn(attn_[l.idx], cur);
         }

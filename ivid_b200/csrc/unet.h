@@ -58,7 +58,14 @@ struct AttnBlockDef {
   GnW gn;
   ConvW qkv, proj;
 };
-struct LayerRef { int kind; int idx; };   // kind 1 = ResBlock, 2 = AttentionBlock
+struct ResampleDef {       // plain Downsample2d / Upsample2d layer (resblock_updown=False, adm.py:60-117)
+  std::string pfx;         // layer name ("input_blocks.3.0", "output_blocks.2.1")
+  int C = 0;
+  int mode = 0;            // 1 up (nearest 2x [+ conv 3x3]), 2 down (conv 3x3 stride 2, or AvgPool2d(2))
+  bool conv = false;       // conv_resample
+  ConvW w;                 // op / conv weights, packed as an ordinary 3x3 conv
+};
+struct LayerRef { int kind; int idx; };   // kind 1 = ResBlock, 2 = AttentionBlock, 3 = plain resampling layer
 struct BlockDef { std::vector<LayerRef> layers; bool is_input = false; bool is_output = false; };
 
 struct Plan;
@@ -112,6 +119,7 @@ class Unet {
   std::map<std::string, int> pindex_;
   std::vector<ResBlockDef> res_;
   std::vector<AttnBlockDef> attn_;
+  std::vector<ResampleDef> resample_;
   std::vector<BlockDef> blocks_;     // input blocks (block 0 = input conv, no layers), middle, output blocks in order
   int film_total_ = 0;
   int in_ch_stem_ = 0;               // channels after the input conv

@@ -61,7 +61,9 @@ def _topology(cfg: dict):
             chs.append(ch)
             ib += 1
         if level != len(mult) - 1:
-            blocks.append({"group": "input", "prefix": f"input_blocks.{ib}", "layers": [("res", f"input_blocks.{ib}.0", ch, ch, "down")]})
+            # adm.py:398-414: a "down" ResBlock, or (resblock_updown=False) a plain Downsample2d
+            down = ("res", f"input_blocks.{ib}.0", ch, ch, "down") if c["resblock_updown"] else ("down", f"input_blocks.{ib}.0", ch)
+            blocks.append({"group": "input", "prefix": f"input_blocks.{ib}", "layers": [down]})
             chs.append(ch)
             ib += 1
             ds //= 2
@@ -79,7 +81,8 @@ def _topology(cfg: dict):
                 layers.append(("attn", f"output_blocks.{ob}.{li}", ch))
                 li += 1
             if level and i == nres:
-                layers.append(("res", f"output_blocks.{ob}.{li}", ch, ch, "up"))
+                # adm.py:463-480: an "up" ResBlock, or (resblock_updown=False) a plain Upsample2d
+                layers.append(("res", f"output_blocks.{ob}.{li}", ch, ch, "up") if c["resblock_updown"] else ("up", f"output_blocks.{ob}.{li}", ch))
                 ds *= 2
             blocks.append({"group": "output", "prefix": f"output_blocks.{ob}", "layers": layers})
             ob += 1
@@ -122,6 +125,12 @@ def unet_param_shapes(cfg: dict) -> Dict[str, tuple]:
                 if cin != cout:
                     out[p + ".skip_connection.weight"] = (cout, cin, 1, 1)
                     out[p + ".skip_connection.bias"] = (cout,)
+            elif l[0] in ("down", "up"):
+                _, p, ch = l
+                if c["conv_resample"]:      # Downsample2d.op (adm.py:111) / Upsample2d.conv (adm.py:81)
+                    sub = ".op" if l[0] == "down" else ".conv"
+                    out[p + sub + ".weight"] = (ch, ch, 3, 3)
+                    out[p + sub + ".bias"] = (ch,)
             else:
                 _, p, ch = l
                 out[p + ".norm.weight"] = (ch,)
@@ -244,6 +253,13 @@ def unet_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, times:
                 h = F.conv2d(h, sd[l[1] + ".weight"], sd[l[1] + ".bias"], padding=1)
             elif l[0] == "res":
                 h = _resblock(h, emb, sd, l[1], l[4], groups)
+            elif l[0] == "down":      # Downsample2d.forward (adm.py:115-117): conv 3x3 stride 2 pad 1, or AvgPool2d(2)
+                h = (F.conv2d(h, sd[l[1] + ".op.weight"], sd[l[1] + ".op.bias"], stride=2, padding=1) if c["conv_resample"]
+                     else F.avg_pool2d(h, 2))
+            elif l[0] == "up":        # Upsample2d.forward (adm.py:86-91): nearest x2, then conv 3x3 if conv_resample
+                h = F.interpolate(h, scale_factor=2, mode="nearest")
+                if c["conv_resample"]:
+                    h = F.conv2d(h, sd[l[1] + ".conv.weight"], sd[l[1] + ".conv.bias"], padding=1)
             else:
                 hc = head_ch if head_ch != -1 else l[2] // c["num_heads"]
                 h = _attention(h, sd, l[1], groups, hc)

@@ -1,4 +1,5 @@
-"""Golden eps of the UNMODIFIED reference UNet for backbone options no shipped config sets (adm.py:214-221 use_scale_shift_norm=False),
+"""Golden eps of the UNMODIFIED reference UNet for backbone options no shipped config sets (adm.py:214-221 use_scale_shift_norm=False;
+adm.py:409,475 resblock_updown=False with Downsample2d / Upsample2d, with and without conv_resample),
 on the tiny test architecture with the oracle's synthetic weights; pins the oracle's branch for them.
 
     python tests/golden/make_options_golden.py        # needs /root/reference; writes tests/golden/options_golden.npz
@@ -16,7 +17,8 @@ import make_golden as mg          # noqa: E402  (easydict shim + reference impor
 from oracle import unet_ref       # noqa: E402
 
 out = {}
-for tag, extra in (("noshift", dict(use_scale_shift_norm=False)),):
+for tag, extra in (("noshift", dict(use_scale_shift_norm=False)), ("plainconv", dict(resblock_updown=False, conv_resample=True)),
+                   ("plainpool", dict(resblock_updown=False, conv_resample=False, use_scale_shift_norm=False))):
     cfg = dict(mg.TINY, **extra)
     sd = unet_ref.make_synthetic_state_dict(cfg, seed=77)
     net = mg.ref_model(cfg, sd)

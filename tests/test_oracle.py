@@ -65,15 +65,21 @@ def test_sampler_oracle_steps(golden):
                        torch.from_numpy(golden["sr_cond_inputs"]))
 
 
-def test_unet_oracle_option_without_scale_shift_norm():
-    """use_scale_shift_norm=False (adm.py:176, 219-221: h = out_layers(h + emb_out)) against the unmodified reference's eps
-    (tests/golden/options_golden.npz, made by tests/golden/make_options_golden.py)."""
+@pytest.mark.parametrize("tag", ["noshift", "plainconv", "plainpool"])
+def test_unet_oracle_backbone_options(tag):
+    """Backbone options no shipped config sets, against the unmodified reference's eps (tests/golden/options_golden.npz, made by
+    tests/golden/make_options_golden.py): use_scale_shift_norm=False (adm.py:176, 219-221: h = out_layers(h + emb_out)),
+    resblock_updown=False with Downsample2d / Upsample2d (adm.py:60-117, 409, 475) with and without conv_resample."""
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options_golden.npz"))
-    cfg = json.loads(bytes(g["noshift_cfg"]).decode())
-    assert cfg["use_scale_shift_norm"] is False
+    cfg = json.loads(bytes(g[f"{tag}_cfg"]).decode())
     sd = unet_ref.make_synthetic_state_dict(cfg, seed=77)
-    assert sd["input_blocks.1.0.emb_layers.1.weight"].shape[0] == sd["input_blocks.1.0.out_layers.0.weight"].shape[0]
-    y = unet_ref.unet_forward(cfg, sd, torch.from_numpy(g["noshift_x"]), torch.from_numpy(g["noshift_t"]), torch.from_numpy(g["noshift_c"]))
-    ref = torch.from_numpy(g["noshift_eps"])
+    if not cfg.get("use_scale_shift_norm", True):
+        assert sd["input_blocks.1.0.emb_layers.1.weight"].shape[0] == sd["input_blocks.1.0.out_layers.0.weight"].shape[0]
+    if tag == "plainconv":
+        assert "input_blocks.2.0.op.weight" in sd and "output_blocks.1.2.conv.weight" in sd
+    if tag == "plainpool":
+        assert not any(".op." in k or k.endswith(".conv.weight") for k in sd)
+    y = unet_ref.unet_forward(cfg, sd, torch.from_numpy(g[f"{tag}_x"]), torch.from_numpy(g[f"{tag}_t"]), torch.from_numpy(g[f"{tag}_c"]))
+    ref = torch.from_numpy(g[f"{tag}_eps"])
     assert float((y - ref).norm() / ref.norm()) < 1e-5
