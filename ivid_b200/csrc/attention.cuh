@@ -50,7 +50,9 @@ attention_kernel_v1(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   using Cfg = AttnCfg;
   constexpr int KV = Cfg::KV;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip would turn every later access into
+  // a generic LD / ST with 64-bit address arithmetic instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + Cfg::Q_BYTES;                       // stage s: K at sKV + s*2*KV_BYTES, V right after
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::STAGES * 2 * Cfg::KV_BYTES);
@@ -249,7 +251,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   using Cfg = AttnCfg2;
   constexpr int KV = Cfg::KV, ST = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip would turn every later access into
+  // a generic LD / ST with 64-bit address arithmetic instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + Cfg::Q_BYTES;                       // stage s: K at sKV + s*2*KV_BYTES, V right after
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ST * 2 * Cfg::KV_BYTES);

@@ -44,6 +44,10 @@ struct ConvGemmParams {
   int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
+  int contig;                  // 1: a CTA (pair) owns a CONTIGUOUS range of the work list, column block slow / pixel tile fast, so that
+                               // its consecutive tiles belong to the same (sample, column block) and the GroupNorm statistics are
+                               // summed in registers and flushed with ONE pair of fp64 atomics per channel and sample instead of
+                               // one per tile (the per-tile atomics cost 2.7 ms of a 22 ms step: profiles/bench_r02q_dbg*.json)
   int res3;                    // epi_tma == 1 with a residual: THREE residual tiles in flight per epilogue warp (the output staging
                                // tile is then single-buffered): 48 instead of 32 KB of residual reads in flight per SM
   int mc_n, mc_m;              // cluster-multicast mode (kMc): cluster = mc_m pixel tiles x mc_n column blocks
@@ -121,7 +125,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     for (int i = 0; i < p.mc_m; ++i) col_mask |= static_cast<uint16_t>(1u << (i * p.mc_n + mc_rn));
   }
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip would turn every later access into
+  // a generic LD / ST with 64-bit address arithmetic instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_smem = smem + (kSlab ? Cfg::SLAB_OPER_BYTES : STAGES * Cfg::STAGE_BYTES);     // 1024-aligned (TMA 128B swizzle)
   uint8_t* bar_area = stage_smem + Cfg::EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);
@@ -169,9 +175,22 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   // work items of this CTA: tiles (kCtas == 1), tile PAIRS of its cluster (kCtas == 2; CTA `rank` owns m-tile 2*pair+rank) or
   // cluster tiles (kMc: mc_m pixel tiles x mc_n column blocks; every CTA of a cluster walks the same item sequence)
   const int mc_size = kMc ? p.mc_n * p.mc_m : 1;
-  const int w_first = kMc ? static_cast<int>(blockIdx.x) / mc_size : (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int w_stride = kMc ? static_cast<int>(gridDim.x) / mc_size : (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int w_limit = p.num_items;
+  int w_first = kMc ? static_cast<int>(blockIdx.x) / mc_size : (kCtas == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  int w_stride = kMc ? static_cast<int>(gridDim.x) / mc_size : (kCtas == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  int w_limit = p.num_items;
+  if (!kMc && p.contig) {
+    // contiguous ranges balanced by cost: a full item counts two units, a half-width tail item one.  CTA c owns the items whose
+    // first unit lies in [ceil(c U / G), ceil((c + 1) U / G))
+    const long long G = w_stride, c = w_first, F = p.full_items;
+    const long long U = 2 * F + (p.num_items - F);
+    auto first_item = [&](long long cc) -> int {
+      const long long u = (cc * U + G - 1) / G;
+      return static_cast<int>(u >= 2 * F ? F + (u - 2 * F) : (u + 1) / 2);
+    };
+    w_first = first_item(c);
+    w_limit = first_item(c + 1);
+    w_stride = 1;
+  }
   // work item -> (pixel-tile index of the CTA (pair), first output column, width)
   auto decode = [&](int w, int& mtp, int& colbase, int& ncols) {
     if constexpr (kMc) {
@@ -190,8 +209,15 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       half = hidx & 1;
       ncols = BN / 2;
     }
-    mtp = f / p.n_blocks;
-    colbase = (f - mtp * p.n_blocks) * BN + half * (BN / 2);
+    if (p.contig) {          // column block slow, pixel tile fast
+      const int m_items = (p.num_tiles / kCtas) / p.n_blocks;
+      const int nb = f / m_items;
+      mtp = f - nb * m_items;
+      colbase = nb * BN + half * (BN / 2);
+    } else {
+      mtp = f / p.n_blocks;
+      colbase = (f - mtp * p.n_blocks) * BN + half * (BN / 2);
+    }
   };
 
   const int kblks = p.seg_chunks[0] * p.seg_taps[0] + p.seg_chunks[1] * p.seg_taps[1] + p.seg_chunks[2] * p.seg_taps[2];
@@ -429,6 +455,48 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     const int box_n0 = (quarter * 32) / (p.TW * p.TH);
     const bool tma_res = p.epi_tma == 1 && p.residual != nullptr && !(p.debug & 2);
     uint32_t res_cnt = 0, res_issued = 0, out_cnt = 0;
+    // GroupNorm statistics of this CTA's consecutive tiles of one (sample, column block): thread t of the 128 epilogue threads owns
+    // columns t and t + 128 of the block; the sums run in fp64 registers and are flushed when the (sample, column block) changes
+    // and after the last item (contig schedule: ~once per CTA and sample; strided schedule: every tile, as before)
+    double acc_s[2] = {0.0, 0.0}, acc_q[2] = {0.0, 0.0};
+    int acc_tn = -1, acc_col0 = 0, acc_ncols = 0;
+    auto stats_flush = [&]() {
+      if (acc_tn < 0) return;
+      const int t = static_cast<int>(threadIdx.x) - 128;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = t + 128 * j;
+        const int col = acc_col0 + c;
+        if (c < acc_ncols && col < p.Cout && acc_tn < p.N && !(p.debug & 1)) {
+          double* st = p.stats + (static_cast<size_t>(acc_tn) * p.Cout + col) * 2;
+          atomicAdd(st, acc_s[j]);
+          atomicAdd(st + 1, acc_q[j]);
+        }
+        acc_s[j] = 0.0; acc_q[j] = 0.0;
+      }
+      acc_tn = -1;
+    };
+    // end-of-tile: combine the four epilogue warps' column sums (stat_smem) into the running sums
+    auto stats_tile = [&](int tn, int colbase, int ncols) {
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (tn != acc_tn || colbase != acc_col0 || ncols != acc_ncols) {
+        stats_flush();
+        acc_tn = tn; acc_col0 = colbase; acc_ncols = ncols;
+      }
+      const int t = static_cast<int>(threadIdx.x) - 128;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = t + 128 * j;
+        if (c < ncols) {
+          float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
+          acc_s[j] += static_cast<double>(ssum);
+          acc_q[j] += static_cast<double>(qsum);
+        }
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    };
     const uint32_t my_tiles = (w_first < w_limit) ? static_cast<uint32_t>((w_limit - w_first + w_stride - 1) / w_stride) : 0u;
     // this CTA's items: first `my_full` full-width ones (NCH chunks each), then half-width ones (NCH / 2 chunks each)
     const uint32_t my_full = (p.full_items > w_first) ? static_cast<uint32_t>((p.full_items - w_first + w_stride - 1) / w_stride) : 0u;
@@ -592,22 +660,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             }
           }
         }
-        if (do_stats && p.TN == 1) {
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          const int t = threadIdx.x - 128;
-          for (int c = t; c < ncols; c += 128) {
-            const int col = colbase + c;
-            if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
-              float ssum = 0.f, qsum = 0.f;
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
-              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
-              atomicAdd(st, static_cast<double>(ssum));
-              atomicAdd(st + 1, static_cast<double>(qsum));
-            }
-          }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
+        if (do_stats && p.TN == 1) stats_tile(tn, colbase, ncols);
       } else if (p.epi_tma == 2) {
         // TMA epilogue, fp16 NHWC output (qkv projections, ResBlock hidden tensor): 64 columns per bulk store
         // ([32 px][64 ch] fp16 = 128-byte rows); no residual on these paths.
@@ -665,22 +718,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             }
           }
         }
-        if (do_stats && p.TN == 1) {
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          const int t = threadIdx.x - 128;
-          for (int c = t; c < ncols; c += 128) {
-            const int col = colbase + c;
-            if (col < p.Cout && n_warp < p.N && !(p.debug & 1)) {
-              float ssum = 0.f, qsum = 0.f;
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
-              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
-              atomicAdd(st, static_cast<double>(ssum));
-              atomicAdd(st + 1, static_cast<double>(qsum));
-            }
-          }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
+        if (do_stats && p.TN == 1) stats_tile(tn, colbase, ncols);
       } else {
         // Coalesced epilogue: the warp's 32 rows x 32 columns chunk goes TMEM -> registers (row per lane) -> XOR-swizzled
         // shared memory -> registers (8 lanes per row, 4 columns each), so every global access is a full 128-byte row
@@ -781,25 +819,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             }
           }
         }
-        if (do_stats && p.TN == 1) {
-          // combine the four epilogue warps (same sample when TN == 1), then one double atomic per (column, moment)
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          const int t = threadIdx.x - 128;
-          for (int c = t; c < ncols; c += 128) {
-            const int col = colbase + c;
-            if (col < p.Cout && n_warp < p.N) {
-              float ssum = 0.f, qsum = 0.f;
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) { ssum += stat_smem[(w4 * 2 + 0) * BN + c]; qsum += stat_smem[(w4 * 2 + 1) * BN + c]; }
-              double* st = p.stats + (static_cast<size_t>(tn) * p.Cout + col) * 2;
-              if (!(p.debug & 1)) {
-                atomicAdd(st, static_cast<double>(ssum));
-                atomicAdd(st + 1, static_cast<double>(qsum));
-              }
-            }
-          }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
+        if (do_stats && p.TN == 1) stats_tile(tn, colbase, ncols);
       }
       tc_fence_before();
       __syncwarp();
@@ -809,6 +829,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    stats_flush();
     if (p.epi_tma && lane == 0) tma_store_wait_all();
   }
 

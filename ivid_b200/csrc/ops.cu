@@ -253,6 +253,9 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     M.out = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     p.epi_tma = 2;
   }
+  // contiguous work ranges + running GroupNorm statistics (conv_gemm.cuh, ConvGemmParams::contig); IVID_CONV_STRIDED=1 restores the
+  // round-robin schedule with one pair of atomics per tile and channel (read per plan build)
+  p.contig = (l->mc == 0 && getenv("IVID_CONV_STRIDED") == nullptr) ? 1 : 0;
   // deeper residual prefetch (three tiles in flight per epilogue warp, single output staging tile): opt-in A/B
   p.res3 = (p.epi_tma == 1 && d.residual != nullptr && getenv("IVID_RES3") != nullptr && getenv("IVID_RES3")[0] == '1') ? 1 : 0;
   // fused statistics are produced by the TMA epilogues only

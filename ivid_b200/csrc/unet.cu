@@ -831,7 +831,7 @@ Plan* Unet::build_plan(int N) {
       Act out = new_act(r.C, Ho, Wo);
       alloc32(out);
       if (r.conv) {
-        IVID_REQUIRE(x.d16 != nullptr, "internal: resampling conv needs the fp16 copy of its input");
+        IVID_REQUIRE(!create || x.d16 != nullptr, "internal: resampling conv needs the fp16 copy of its input");
         const void* x16 = x.d16;
         const int H = x.H, Wd = x.W, C = r.C;
         ConvDesc d;
