@@ -255,7 +255,11 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   }
   // contiguous work ranges + running GroupNorm statistics (conv_gemm.cuh, ConvGemmParams::contig); IVID_CONV_STRIDED=1 restores the
   // round-robin schedule with one pair of atomics per tile and channel (read per plan build)
-  p.contig = (l->mc == 0 && getenv("IVID_CONV_STRIDED") == nullptr) ? 1 : 0;
+  // Measured (profiles/per_op_r02r_*.json, same box): with ONE column block (Cout <= BN: the 128^2 / 64^2 levels, where a sample
+  // spans 32-128 tiles) the contiguous ranges are 2-8 % faster; with several column blocks (32^2 and below) they are 25-50 %
+  // slower than the round-robin order, in which the CTAs that share an activation tile run at the same time.
+  p.contig = (l->mc == 0 && p.n_blocks == 1 && p.full_items == p.num_items && getenv("IVID_CONV_STRIDED") == nullptr) ? 1 : 0;
+  if (getenv("IVID_CONV_CONTIG_ALL") != nullptr && l->mc == 0) p.contig = 1;
   // deeper residual prefetch (three tiles in flight per epilogue warp, single output staging tile): opt-in A/B
   p.res3 = (p.epi_tma == 1 && d.residual != nullptr && getenv("IVID_RES3") != nullptr && getenv("IVID_RES3")[0] == '1') ? 1 : 0;
   // fused statistics are produced by the TMA epilogues only
