@@ -503,32 +503,39 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
     const uint32_t my_full_c = my_full < my_tiles ? my_full : my_tiles;
     constexpr uint32_t NCHH = NCH >= 2 ? NCH / 2 : 1;
     const uint32_t total_seq = my_full_c * NCH + (my_tiles - my_full_c) * NCHH;
-    auto issue_res = [&](uint32_t seq) {      // lane 0: residual tile of chunk `seq` of this CTA's chunk stream
-      uint32_t item, k2u;
-      if (seq < my_full_c * NCH) { item = seq / NCH; k2u = seq % NCH; }
-      else { const uint32_t s2 = seq - my_full_c * NCH; item = my_full_c + s2 / NCHH; k2u = s2 % NCHH; }
-      const int w2 = w_first + static_cast<int>(item) * w_stride;
-      const int k2 = static_cast<int>(k2u);
+    // Residual prefetch cursor: the residual tiles are requested in the order the chunks are consumed (items of this CTA, 32-column
+    // chunks of an item).  The cursor keeps the decoded tile of the item it is in, so the integer divisions of the work-item
+    // decode run once per item and not once per chunk (they sat on the single epilogue warp's critical path).
+    uint32_t pf_item = 0;
+    int pf_k = 0, pf_nch = 0, pf_col = 0, pf_x = 0, pf_y = 0, pf_n = 0;
+    auto pf_load_item = [&]() {
+      const int w2 = w_first + static_cast<int>(pf_item) * w_stride;
       int mtp2, colbase2, ncols2;
       decode(w2, mtp2, colbase2, ncols2);
       const int mt2 = mtp2 * kCtas + static_cast<int>(cta_rank);
       const int tn2 = mt2 / tiles_per_img, rem2 = mt2 - tn2 * tiles_per_img;
       const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
+      pf_nch = ncols2 / 32; pf_col = colbase2; pf_k = 0;
+      pf_x = p.res_up ? (tw2 * p.TW) >> 1 : tw2 * p.TW;
+      pf_y = p.res_up ? (th2 * p.TH + box_h0) >> 1 : th2 * p.TH + box_h0;
+      pf_n = tn2 * p.TN + box_n0;
+    };
+    auto issue_res = [&](uint32_t seq) {      // lane 0: residual tile of chunk `seq` (== the cursor position) of this CTA's chunk stream
       uint64_t* bar = &res_bar[seq % RD];
-      if (p.res_up) {
-        // the warp's 16 x 2 output pixels are the 2x2 replicas of 8 x 1 source pixels: a [32 ch][8][1][1] box (1 KB)
-        mbar_arrive_expect_tx(bar, 1024);
-        tma_load_4d(&maps.res, bar, res_tile(seq), colbase2 + k2 * 32, (tw2 * p.TW) >> 1,
-                    (th2 * p.TH + box_h0) >> 1, tn2 * p.TN + box_n0);
-      } else {
-        mbar_arrive_expect_tx(bar, 4096);
-        tma_load_4d(&maps.res, bar, res_tile(seq), colbase2 + k2 * 32, tw2 * p.TW, th2 * p.TH + box_h0,
-                    tn2 * p.TN + box_n0);
+      // res_up: the warp's 16 x 2 output pixels are the 2x2 replicas of 8 x 1 source pixels: a [32 ch][8][1][1] box (1 KB)
+      mbar_arrive_expect_tx(bar, p.res_up ? 1024u : 4096u);
+      tma_load_4d(&maps.res, bar, res_tile(seq), pf_col + pf_k * 32, pf_x, pf_y, pf_n);
+      if (++pf_k == pf_nch) {
+        ++pf_item;
+        if (pf_item < my_tiles) pf_load_item();
       }
     };
     if constexpr (CH == 32) {
       if (tma_res) {
-        if (lane == 0) for (uint32_t i = 0; i < RD && i < total_seq; ++i) issue_res(i);
+        if (lane == 0 && my_tiles > 0) {
+          pf_load_item();
+          for (uint32_t i = 0; i < RD && i < total_seq; ++i) issue_res(i);
+        }
         res_issued = total_seq < RD ? total_seq : RD;
       }
     }
@@ -543,6 +550,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       const int tw = rem - th * p.tiles_w;
       const int n = tn * p.TN + pn, h = th * p.TH + ph, w = tw * p.TW + pw;
       const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+      const bool all_valid = __all_sync(0xffffffffu, valid);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -613,7 +621,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
               const float4 t = p.res_up ? rb[rrow * 8 + (j ^ rrow)] : rb[pos];
               v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
-            if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the batch tail: clipped by TMA, zero for the statistics
+            if (!all_valid && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the batch tail: clipped by TMA, zero for the statistics
             ob[pos] = v;
             if (want16) {
               if (j & 1) {

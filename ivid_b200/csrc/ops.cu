@@ -253,12 +253,12 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     M.out = make_tensor_map(CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     p.epi_tma = 2;
   }
-  // contiguous work ranges + running GroupNorm statistics (conv_gemm.cuh, ConvGemmParams::contig); IVID_CONV_STRIDED=1 restores the
-  // round-robin schedule with one pair of atomics per tile and channel (read per plan build)
-  // Measured (profiles/per_op_r02r_*.json, same box): with ONE column block (Cout <= BN: the 128^2 / 64^2 levels, where a sample
-  // spans 32-128 tiles) the contiguous ranges are 2-8 % faster; with several column blocks (32^2 and below) they are 25-50 %
-  // slower than the round-robin order, in which the CTAs that share an activation tile run at the same time.
-  p.contig = (l->mc == 0 && p.n_blocks == 1 && p.full_items == p.num_items && getenv("IVID_CONV_STRIDED") == nullptr) ? 1 : 0;
+  // contiguous work ranges + running GroupNorm statistics (conv_gemm.cuh, ConvGemmParams::contig)
+  // Measured (profiles/per_op_r02r_*.json, bench_r02s_*): with ONE column block (Cout <= BN: the 128^2 / 64^2 levels) the contiguous
+  // ranges are 2-8 % faster per isolated launch and +-0 inside the step; with several column blocks (32^2 and below) they are
+  // 25-50 % slower than the round-robin order, in which the CTAs that share an activation tile run at the same time.  Opt-in:
+  // IVID_CONV_CONTIG=1 (single-column-block layers) / IVID_CONV_CONTIG_ALL=1 (read per plan build).
+  p.contig = (l->mc == 0 && p.n_blocks == 1 && p.full_items == p.num_items && getenv("IVID_CONV_CONTIG") != nullptr) ? 1 : 0;
   if (getenv("IVID_CONV_CONTIG_ALL") != nullptr && l->mc == 0) p.contig = 1;
   // deeper residual prefetch (three tiles in flight per epilogue warp, single output staging tile): opt-in A/B
   p.res3 = (p.epi_tma == 1 && d.residual != nullptr && getenv("IVID_RES3") != nullptr && getenv("IVID_RES3")[0] == '1') ? 1 : 0;

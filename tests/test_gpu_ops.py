@@ -45,21 +45,21 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=["default", "multicast", "slab", "strided"])
+@pytest.fixture(params=["default", "multicast", "slab", "contig"])
 def conv_mode(request, monkeypatch):
     """Every conv case runs through the default kernels, through the opt-in cluster-multicast kernel (IVID_MC=1 is read when
     a launch is created; it only takes effect on low-resolution N = 128 layers) and through the 3x3 tap-reuse ("slab") kernel
-    (IVID_SLAB=1, CTA-pair layers with H >= 16); "strided" = the round-robin work schedule (IVID_CONV_STRIDED=1) instead of the
-    default contiguous ranges."""
+    (IVID_SLAB=1, CTA-pair layers with H >= 16); "contig" = contiguous work ranges per CTA (IVID_CONV_CONTIG_ALL=1) instead of the
+    default round-robin schedule."""
     monkeypatch.delenv("IVID_MC", raising=False)
     monkeypatch.delenv("IVID_SLAB", raising=False)
-    monkeypatch.delenv("IVID_CONV_STRIDED", raising=False)
+    monkeypatch.delenv("IVID_CONV_CONTIG_ALL", raising=False)
     if request.param == "multicast":
         monkeypatch.setenv("IVID_MC", "1")
     elif request.param == "slab":
         monkeypatch.setenv("IVID_SLAB", "1")
-    elif request.param == "strided":
-        monkeypatch.setenv("IVID_CONV_STRIDED", "1")
+    elif request.param == "contig":
+        monkeypatch.setenv("IVID_CONV_CONTIG_ALL", "1")
     return request.param
 
 
