@@ -203,6 +203,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Same descriptor with a matrix base offset (bits [49,52)): the phase of the 128-byte swizzle pattern at the start address when
+// the matrix does not start on a 1024-byte (8-row) boundary of the pattern = (start address >> 7) & 7.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes, uint32_t base_offset) {
+  return make_smem_desc_sw128(smem_addr, sbo_bytes, lbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
+}
+
 // Instruction descriptor for kind::f16 (fp16 A/B when bf16==0, fp32 accumulate).
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bool bf16, bool a_mn_major,
                                                       bool b_mn_major) {

@@ -44,6 +44,9 @@ struct ConvGemmParams {
   int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
+  int slab_mode;               // kSlab kernel: 1 = three [18][8]-pixel slabs per chunk (one per horizontal shift, aligned descriptors);
+                               // 2 = ONE [18][16]-pixel slab per chunk, horizontal taps as descriptor starts 128 B apart inside a
+                               // swizzle atom (matrix base offset = dx; 3: same with base offset 0, to probe the hardware rule)
   int contig;                  // 1: a CTA (pair) owns a CONTIGUOUS range of the work list, column block slow / pixel tile fast, so that
                                // its consecutive tiles belong to the same (sample, column block) and the GroupNorm statistics are
                                // summed in registers and flushed with ONE pair of fp64 atomics per channel and sample instead of
@@ -90,7 +93,10 @@ struct ConvGemmCfg {
   static constexpr int SLAB_ROWS = 18;
   static constexpr int SLAB_A_BYTES = SLAB_ROWS * 8 * BK * 2;                  // 18 KB
   static constexpr int SLAB_SA = 3, SLAB_SB = 5;
-  static constexpr int SLAB_OPER_BYTES = SLAB_SA * SLAB_A_BYTES + SLAB_SB * B_BYTES;
+  // mode 2: [18 rows][16 px] slabs (36 KB), two of them, and a four-deep weight ring
+  static constexpr int SLAB2_A_BYTES = SLAB_ROWS * 16 * BK * 2, SLAB2_SA = 2, SLAB2_SB = 4;
+  static constexpr int SLAB1_OPER = SLAB_SA * SLAB_A_BYTES + SLAB_SB * B_BYTES, SLAB2_OPER = SLAB2_SA * SLAB2_A_BYTES + SLAB2_SB * B_BYTES;
+  static constexpr int SLAB_OPER_BYTES = SLAB1_OPER > SLAB2_OPER ? SLAB1_OPER : SLAB2_OPER;
   static constexpr int SMEM_BYTES_SLAB = SLAB_OPER_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;
 };
 
@@ -229,7 +235,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t afull0 = mapa_cluster(smem_u32(&full_bar[0]), 0), bfull0 = mapa_cluster(smem_u32(&bfull_bar[0]), 0);
-      uint8_t* b_ring = smem + Cfg::SLAB_SA * Cfg::SLAB_A_BYTES;
+      const bool wide = p.slab_mode >= 2;
+      const int na = wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
+      const int a_slot = wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      uint8_t* b_ring = smem + na * a_slot;
       for (int w = w_first; w < w_limit; w += w_stride) {
         int mtp, colbase, ncols;
         decode(w, mtp, colbase, ncols);
@@ -248,7 +257,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           mbar_wait(&bempty_bar[sb], pb ^ 1);
           if (cta_rank == 0) mbar_arrive_expect_tx(&bfull_bar[sb], 2 * b_bytes);
           tma_load_2d_2sm(mapB, bfull0 + sb * 8, b_ring + sb * Cfg::B_BYTES, kcol, bcol);
-          if (++sb == NB) { sb = 0; pb ^= 1; }
+          if (++sb == nb) { sb = 0; pb ^= 1; }
         };
 #pragma unroll 1
         for (int seg = 0; seg < 3; ++seg) {
@@ -257,21 +266,28 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           if (chunks == 0) continue;
 #pragma unroll 1
           for (int ch = 0; ch < chunks; ++ch) {
-            if (taps == 9) {
+            if (taps == 9 && wide) {
+              mbar_wait(&empty_bar[sa], pa ^ 1);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB2_A_BYTES);
+              tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
+              if (++sa == na) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+              for (int t = 0; t < 9; ++t) load_b(seg_base + (t * chunks + ch) * 64);
+            } else if (taps == 9) {
 #pragma unroll 1
               for (int dx = 0; dx < 3; ++dx) {
                 mbar_wait(&empty_bar[sa], pa ^ 1);
                 if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB_A_BYTES);
-                tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * Cfg::SLAB_A_BYTES, ch * 64, w0 + dx - 1, h0 - 1, n0);
-                if (++sa == NA) { sa = 0; pa ^= 1; }
+                tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0 + dx - 1, h0 - 1, n0);
+                if (++sa == na) { sa = 0; pa ^= 1; }
 #pragma unroll 1
                 for (int dy = 0; dy < 3; ++dy) load_b(seg_base + ((dy * 3 + dx) * chunks + ch) * 64);
               }
             } else {
               mbar_wait(&empty_bar[sa], pa ^ 1);
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::A_BYTES);
-              tma_load_4d_2sm(&maps.a[seg], afull0 + sa * 8, smem + sa * Cfg::SLAB_A_BYTES, ch * 64, w0, h0, n0);
-              if (++sa == NA) { sa = 0; pa ^= 1; }
+              tma_load_4d_2sm(&maps.a[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0, h0, n0);
+              if (++sa == na) { sa = 0; pa ^= 1; }
               load_b(seg_base + ch * 64);
             }
           }
@@ -288,17 +304,21 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t b_ring = smem_u32(smem + Cfg::SLAB_SA * Cfg::SLAB_A_BYTES);
+      const bool wide = p.slab_mode >= 2;
+      const int na = wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
+      const int a_slot = wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      const uint32_t b_ring = smem_u32(smem + na * a_slot);
       for (int w = w_first; w < w_limit; w += w_stride) {
         const uint32_t idesc = (w >= p.full_items) ? idesc_half : idesc_full;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         uint32_t accum = 0;
-        auto tap = [&](uint32_t a_addr) {          // one weight tile against the activation rows starting at a_addr
+        // one weight tile against the 128 activation rows starting at a_addr (8-row groups `sbo` bytes apart)
+        auto tap = [&](uint32_t a_addr, uint32_t sbo = 1024, uint32_t bo = 0) {
           mbar_wait(&bfull_bar[sb], pb);
           tc_fence_after();
-          const uint64_t da = make_smem_desc_sw128(a_addr, 1024, 16);
+          const uint64_t da = make_smem_desc_sw128_bo(a_addr, sbo, 16, bo);
           const uint64_t db = make_smem_desc_sw128(b_ring + sb * Cfg::B_BYTES, 1024, 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -306,7 +326,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             accum = 1u;
           }
           tc_commit_2sm(&bempty_bar[sb]);
-          if (++sb == NB) { sb = 0; pb ^= 1; }
+          if (++sb == nb) { sb = 0; pb ^= 1; }
         };
 #pragma unroll 1
         for (int seg = 0; seg < 3; ++seg) {
@@ -315,20 +335,28 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           if (chunks == 0) continue;
 #pragma unroll 1
           for (int ch = 0; ch < chunks; ++ch) {
-            const int nslab = taps == 9 ? 3 : 1;
+            const int nslab = (taps == 9 && !wide) ? 3 : 1;
 #pragma unroll 1
             for (int dx = 0; dx < nslab; ++dx) {
               mbar_wait(&full_bar[sa], pa);
               tc_fence_after();
-              const uint32_t a_addr = smem_u32(smem + sa * Cfg::SLAB_A_BYTES);
-              if (taps == 9) {
+              const uint32_t a_addr = smem_u32(smem + sa * a_slot);
+              if (taps == 9 && wide) {
+                // slab row (2048 B = 16 px) dy = image row y0 - 1 + dy; pixel column dx = image column x0 - 1 + dx: the tile row of
+                // tap (dy, dx) starts dx * 128 B into the swizzle atom of that slab row
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                  const uint32_t tdy = t / 3, tdx = t - 3 * tdy;
+                  tap(a_addr + tdy * 2048 + tdx * 128, 2048, p.slab_mode == 2 ? tdx : 0u);
+                }
+              } else if (taps == 9) {
 #pragma unroll 1
                 for (int dy = 0; dy < 3; ++dy) tap(a_addr + dy * 1024);      // slab row dy = image row y0 - 1 + dy
               } else {
                 tap(a_addr);
               }
               tc_commit_2sm(&empty_bar[sa]);
-              if (++sa == NA) { sa = 0; pa ^= 1; }
+              if (++sa == na) { sa = 0; pa ^= 1; }
             }
           }
         }

@@ -126,6 +126,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     const int slab_mode = getenv("IVID_SLAB") ? atoi(getenv("IVID_SLAB")) : 0;      // read per plan build (tests switch it)
     if (slab_mode && l->ctas == 2 && d.taps0 == 9 && d.H >= 16 && d.W >= 16 && !d.residual_up) {
       l->slab = 1;
+      p.slab_mode = slab_mode >= 2 ? slab_mode : 1;
       p.TW = 8; p.TH = 16; p.TN = 1;
       p.tiles_w = d.W / p.TW; p.tiles_h = d.H / p.TH; p.tiles_n = d.N;
     }
@@ -207,9 +208,10 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   }
   if (l->mc == 0) { M.a_mc[0] = M.a[0]; M.a_mc[1] = M.a[0]; M.a_mc[2] = M.a[0]; M.b_mc = M.b; }
   if (l->slab) {
-    M.a_mc[0] = make_act_map(d.act0, d.N, d.H, d.W, d.C0, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
-    if (d.C1 > 0 && d.taps1 == 9) M.a_mc[1] = make_act_map(d.act1, d.N, d.H, d.W, d.C1, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
-    if (d.C2 > 0 && d.taps2 == 9) M.a_mc[2] = make_act_map(d.act2, d.N, d.H, d.W, d.C2, 8, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+    const int sw = p.slab_mode >= 2 ? 16 : 8;        // slab width in pixels
+    M.a_mc[0] = make_act_map(d.act0, d.N, d.H, d.W, d.C0, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+    if (d.C1 > 0 && d.taps1 == 9) M.a_mc[1] = make_act_map(d.act1, d.N, d.H, d.W, d.C1, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
+    if (d.C2 > 0 && d.taps2 == 9) M.a_mc[2] = make_act_map(d.act2, d.N, d.H, d.W, d.C2, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
   }
   // TMA epilogue for fp32 NHWC outputs: one box = the 32 pixels of an epilogue warp x 32 channels
   M.out = M.a[0]; M.res = M.a[0]; M.out16 = M.a[0];
