@@ -47,6 +47,12 @@ struct ConvGemmParams {
   int slab_mode;               // kSlab kernel: 1 = three [18][8]-pixel slabs per chunk (one per horizontal shift, aligned descriptors);
                                // 2 = ONE [18][16]-pixel slab per chunk, horizontal taps as descriptor starts 128 B apart inside a
                                // swizzle atom (matrix base offset = dx; 3: same with base offset 0, to probe the hardware rule)
+  int fold;                    // kSlab mode 2 only: the GroupNorm affine + SiLU of the 3x3 segments is applied to the raw fp16 slab in shared
+                               // memory by the two spare warps (y = silu(A x + B), (A, B) per (sample, channel) from fold_ab; pixels
+                               // outside the image stay zero), so the separate GroupNorm-apply pass of that operand disappears
+  const float2* fold_ab;       // [N][fold_C]
+  int fold_C;                  // channels of the coefficient table (virtual concat width)
+  int fold_off[3];             // channel offset of each segment in the table; < 0: segment is consumed as loaded
   int contig;                  // 1: a CTA (pair) owns a CONTIGUOUS range of the work list, column block slow / pixel tile fast, so that
                                // its consecutive tiles belong to the same (sample, column block) and the GroupNorm statistics are
                                // summed in registers and flushed with ONE pair of fp64 atomics per channel and sample instead of
@@ -143,7 +149,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   uint64_t* tmem_full = bempty_bar + NB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;                               // [4 warps][2 or 3 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 12);
+  uint64_t* araw_bar = res_full + 12;                                // [NA] fold mode: this CTA's raw slab has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw_bar + NA);
   float* stat_smem = reinterpret_cast<float*>(bar_area + Cfg::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -155,8 +162,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NA; ++s) {
-      mbar_init(&full_bar[s], 1);
+      // fold mode: the MMA thread's "operand ready" barrier counts one arrive per CTA of the pair (its transform warps)
+      mbar_init(&full_bar[s], (kSlab && p.fold) ? 2u : 1u);
       mbar_init(&empty_bar[s], kMc ? static_cast<uint32_t>(p.mc_n + p.mc_m - 1) : 1u);
+      mbar_init(&araw_bar[s], 1);
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&bfull_bar[s], 1);
@@ -268,8 +277,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
           for (int ch = 0; ch < chunks; ++ch) {
             if (taps == 9 && wide) {
               mbar_wait(&empty_bar[sa], pa ^ 1);
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB2_A_BYTES);
-              tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
+              if (p.fold) {          // each CTA's slab lands on its own barrier; its transform warps release it to the MMA thread
+                mbar_arrive_expect_tx(&araw_bar[sa], Cfg::SLAB2_A_BYTES);
+                tma_load_4d(&maps.a_mc[seg], &araw_bar[sa], smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
+              } else {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB2_A_BYTES);
+                tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
+              }
               if (++sa == na) { sa = 0; pa ^= 1; }
 #pragma unroll 1
               for (int t = 0; t < 9; ++t) load_b(seg_base + (t * chunks + ch) * 64);
@@ -285,8 +299,13 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
               }
             } else {
               mbar_wait(&empty_bar[sa], pa ^ 1);
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::A_BYTES);
-              tma_load_4d_2sm(&maps.a[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0, h0, n0);
+              if (p.fold) {
+                mbar_arrive_expect_tx(&araw_bar[sa], Cfg::A_BYTES);
+                tma_load_4d(&maps.a[seg], &araw_bar[sa], smem + sa * a_slot, ch * 64, w0, h0, n0);
+              } else {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::A_BYTES);
+                tma_load_4d_2sm(&maps.a[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0, h0, n0);
+              }
               if (++sa == na) { sa = 0; pa ^= 1; }
               load_b(seg_base + ch * 64);
             }
@@ -362,6 +381,76 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         }
         tc_commit_2sm(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (kSlab && (warp == 2 || warp == 3)) {
+    // ===================================== operand transform (fold mode): GroupNorm affine + SiLU in place =====================
+    if constexpr (kSlab) {
+      if (p.fold) {
+        const int tt = static_cast<int>(threadIdx.x) - 64;       // 0..63
+        const int cq = tt & 7, pq = tt >> 3;                     // logical 16-byte channel chunk, pixel phase
+        const int na = Cfg::SLAB2_SA, a_slot = Cfg::SLAB2_A_BYTES;
+        int sa = 0;
+        uint32_t pa = 0;
+        const uint32_t ready0 = mapa_cluster(smem_u32(&full_bar[0]), 0);
+        for (int w = w_first; w < w_limit; w += w_stride) {
+          int mtp, colbase, ncols;
+          decode(w, mtp, colbase, ncols);
+          const int mt = mtp * 2 + static_cast<int>(cta_rank);
+          const int tn = mt / tiles_per_img;
+          const int rem = mt - tn * tiles_per_img;
+          const int th = rem / p.tiles_w;
+          const int tw = rem - th * p.tiles_w;
+          const int n0 = tn * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
+#pragma unroll 1
+          for (int seg = 0; seg < 3; ++seg) {
+            const int taps = p.seg_taps[seg];
+            const int chunks = p.seg_chunks[seg];
+            if (chunks == 0) continue;
+            const bool xform = taps == 9 && p.fold_off[seg] >= 0;
+#pragma unroll 1
+            for (int ch = 0; ch < chunks; ++ch) {
+              float cA[8], cB[8];
+              if (xform) {      // this thread's 8 channels of the chunk: issued before the wait for the slab
+                const float4* ab = reinterpret_cast<const float4*>(p.fold_ab + static_cast<size_t>(n0) * p.fold_C + p.fold_off[seg] + ch * 64 + cq * 8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 v = __ldg(ab + i);
+                  cA[2 * i] = v.x; cB[2 * i] = v.y; cA[2 * i + 1] = v.z; cB[2 * i + 1] = v.w;
+                }
+              }
+              mbar_wait(&araw_bar[sa], pa);
+              if (xform) {
+                uint8_t* slab = smem + sa * a_slot;
+                // pixels (srow, px), px = 0..9 (image columns x0-1 .. x0+8), of the [18][16]-pixel slab; 128-byte rows, 16-byte
+                // chunks XOR-swizzled with the row index (TMA SWIZZLE_128B)
+#pragma unroll 2
+                for (int pp = pq; pp < Cfg::SLAB_ROWS * 10; pp += 8) {
+                  const int srow = pp / 10, px = pp - srow * 10;
+                  const int y = h0 - 1 + srow, x = w0 - 1 + px;
+                  if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;        // conv zero padding stays zero
+                  const int r = srow * 16 + px;
+                  uint4* ptr = reinterpret_cast<uint4*>(slab + r * 128 + ((cq ^ (r & 7)) << 4));
+                  const uint4 raw = *ptr;
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    const float y0 = silu_f(fmaf(f.x, cA[2 * j], cB[2 * j]));
+                    const float y1 = silu_f(fmaf(f.y, cA[2 * j + 1], cB[2 * j + 1]));
+                    pk[j] = pack_h2(y0, y1);
+                  }
+                  *ptr = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                fence_proxy_async_smem();      // the tensor core reads the slab through the async proxy
+              }
+              asm volatile("bar.sync 2, 64;\n" ::: "memory");
+              if (tt == 0) mbar_arrive_cluster(ready0 + sa * 8);
+              if (++sa == na) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
       }
     }
   } else if (!kSlab && warp == 0 && lane == 0) {

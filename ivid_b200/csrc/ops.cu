@@ -53,6 +53,17 @@ int conv_pick_bn(int cout_pad, int m_tiles) {
   throw Error(kErrInvalidArgument, "conv: unsupported padded Cout " + std::to_string(cout_pad));
 }
 
+static bool conv_pairs(int m_tiles, int cout_pad) {
+  static const bool pair_ok = getenv("IVID_NO_2CTA") == nullptr;
+  return pair_ok && conv_pick_bn(cout_pad, m_tiles) == 256 && m_tiles % 2 == 0 && m_tiles >= 2;
+}
+bool conv_fold_ok(int N, int H, int W, int cout_pad, bool residual_up) {
+  const char* e = getenv("IVID_FOLD");
+  if (e == nullptr || e[0] != '1') return false;
+  if (H < 16 || W < 16 || residual_up) return false;
+  return conv_pairs(N * (H * W / 128), cout_pad);
+}
+
 template <int BN>
 static void set_conv_attr() {
   static std::once_flag once;
@@ -123,12 +134,20 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     l->ctas = (pair_ok && l->BN == 256 && m_tiles % 2 == 0 && m_tiles >= 2) ? 2 : 1;
     if (l->BN == 256 && l->ctas == 1 && (pair_ok || d.out16 != nullptr)) l->BN = 128;
     // 3x3 tap reuse (conv_gemm_kernel<.., kSlab>): 8 x 16 pixel tiles; not with the upsampled residual (16-wide boxes)
-    const int slab_mode = getenv("IVID_SLAB") ? atoi(getenv("IVID_SLAB")) : 0;      // read per plan build (tests switch it)
+    int slab_mode = getenv("IVID_SLAB") ? atoi(getenv("IVID_SLAB")) : 0;      // read per plan build (tests switch it)
+    if (d.fold_ab != nullptr) slab_mode = 2;
     if (slab_mode && l->ctas == 2 && d.taps0 == 9 && d.H >= 16 && d.W >= 16 && !d.residual_up) {
       l->slab = 1;
       p.slab_mode = slab_mode >= 2 ? slab_mode : 1;
       p.TW = 8; p.TH = 16; p.TN = 1;
       p.tiles_w = d.W / p.TW; p.tiles_h = d.H / p.TH; p.tiles_n = d.N;
+    }
+    p.fold = 0; p.fold_ab = nullptr; p.fold_C = 0; p.fold_off[0] = p.fold_off[1] = p.fold_off[2] = -1;
+    if (d.fold_ab != nullptr) {
+      IVID_REQUIRE(l->slab == 1 && p.slab_mode == 2, "conv: fold mode needs the CTA-pair tap-reuse kernel (see conv_fold_ok)");
+      IVID_REQUIRE(d.fold_C % 8 == 0 && d.fold_off0 % 8 == 0, "conv: fold coefficient table alignment");
+      p.fold = 1; p.fold_ab = static_cast<const float2*>(d.fold_ab); p.fold_C = d.fold_C;
+      p.fold_off[0] = d.fold_off0; p.fold_off[1] = d.C1 > 0 ? d.fold_off1 : -1; p.fold_off[2] = d.C2 > 0 ? d.fold_off2 : -1;
     }
   }
   p.n_blocks = d.cout_pad / l->BN;
@@ -435,6 +454,18 @@ void launch_gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   } else {
     gn_apply_kernel<<<grid, 256, smem, s>>>(p);
   }
+  IVID_CHECK_CUDA(cudaGetLastError());
+}
+void launch_gn_coeff(const GnApplyDesc& d, void* out_ab, cudaStream_t s) {
+  const int C = d.C0 + d.C1;
+  IVID_REQUIRE(C % 8 == 0 && d.groups >= 1 && d.groups <= 64 && C % d.groups == 0, "gn_coeff: channel / group counts");
+  IVID_REQUIRE(d.stats0 != nullptr && d.gamma != nullptr && d.beta != nullptr && out_ab != nullptr, "gn_coeff: statistics / affine parameters missing");
+  GnApplyParams p = GnApplyParams();
+  p.C0 = d.C0; p.C1 = d.C1; p.N = d.N; p.H = d.H; p.W = d.W;
+  p.stats0 = d.stats0; p.stats1 = d.stats1; p.groups = d.groups; p.inv_count = 1.0 / (static_cast<double>(d.H) * d.W);
+  p.eps = d.eps; p.gamma = d.gamma; p.beta = d.beta; p.film = d.film; p.film_ld = d.film_ld; p.film_off = d.film_off;
+  p.film_add = d.film_add ? 1 : 0;
+  gn_coeff_kernel<<<dim3(1, d.N), 256, static_cast<size_t>(C) * 8, s>>>(p, static_cast<float2*>(out_ab));
   IVID_CHECK_CUDA(cudaGetLastError());
 }
 

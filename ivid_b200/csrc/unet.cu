@@ -669,6 +669,17 @@ Plan* Unet::build_plan(int N) {
       pl->ops.push_back([d](cudaStream_t s) { launch_gn_apply(d, s); });
     };
 
+    // GroupNorm folded into the consuming conv (conv_fold_ok): only the per-(sample, channel) coefficients are computed here
+    // (gn_coeff_kernel -> s_ab); the conv reads the RAW fp16 tensor and applies silu(A x + B) in its operand path
+    auto add_fold_coeff = [&](const GnApplyDesc& g) {
+      if (!create) return;
+      GnApplyDesc d = g;
+      d.stats0 = pend.stats0; d.stats1 = pend.stats1; d.groups = pend.groups; d.eps = pend.eps; d.gamma = pend.gamma;
+      d.beta = pend.beta; d.film = pend.film; d.film_ld = pend.film_ld; d.film_off = pend.film_off; d.film_add = pend.film_add;
+      pl->ops.tag("gn_coeff", 0, static_cast<double>(d.N) * (d.C0 + d.C1) * 24, "C" + std::to_string(d.C0 + d.C1));
+      pl->ops.push_back([d, s_ab](cudaStream_t s) { launch_gn_coeff(d, s_ab, s); });
+    };
+
     // ---- embeddings ----
     if (create) {
       const float* freqs = Wf(freqs_off_);
@@ -745,7 +756,8 @@ Plan* Unet::build_plan(int N) {
       g1.N = N; g1.H = H; g1.W = Wd; g1.mode = r.mode; g1.silu = 1;
       g1.out_act = s_a1; g1.out_raw16 = (r.skip_conv && !use16) ? s_xh : nullptr; g1.out_raw32 = need_xr ? s_xr : nullptr;
       IVID_REQUIRE(!(r.skip_conv && r.mode != 0), "internal: up/down ResBlocks keep the channel count");
-      add_apply(g1);
+      const bool fold1 = use16 && x1 == nullptr && conv_fold_ok(N, Ho, Wo, r.conv1.cout_pad, false);
+      if (fold1) add_fold_coeff(g1); else add_apply(g1);
       // conv1 -> h (fp32) ; stats
       bool h_half = false;
       Act h; h.C = r.cout; h.H = Ho; h.W = Wo; h.data = s_h;
@@ -753,6 +765,7 @@ Plan* Unet::build_plan(int N) {
       {
         ConvDesc d;
         d.act0 = s_a1; d.C0 = r.cin; d.taps0 = 9;
+        if (fold1) { d.act0 = x0.d16; d.fold_ab = s_ab; d.fold_C = r.cin; d.fold_off0 = 0; }
         d.weight = W8(r.conv1.w_off); d.cout_pad = r.conv1.cout_pad; d.cout = r.cout; d.bias = Wf(r.conv1.b_off);
         // the hidden tensor only feeds GroupNorm 2: stored as fp16 (half the epilogue and GN traffic); its statistics are
         // taken from the rounded values in the conv epilogue.  Tiny feature maps keep the fp32 + stats-kernel path.
@@ -766,12 +779,14 @@ Plan* Unet::build_plan(int N) {
       GnApplyDesc g2;
       g2.x0 = h.data; g2.x0_half = h_half; g2.C0 = r.cout; g2.N = N; g2.H = Ho; g2.W = Wo; g2.mode = 0; g2.silu = 1;
       g2.out_act = s_a2;
-      add_apply(g2);
+      const bool fold2 = h_half && conv_fold_ok(N, Ho, Wo, r.conv2.cout_pad, res_up);
+      if (fold2) add_fold_coeff(g2); else add_apply(g2);
       // conv2 (+ 1x1 skip as extra K) + residual -> out
       Act out = new_act(r.cout, Ho, Wo);
       {
         ConvDesc d;
         d.act0 = s_a2; d.C0 = r.cout; d.taps0 = 9;
+        if (fold2) { d.act0 = h.data; d.fold_ab = s_ab; d.fold_C = r.cout; d.fold_off0 = 0; }
         if (r.skip_conv && use16) {
           d.act1 = x0.d16; d.C1 = x0.C; d.taps1 = 1;
           if (x1 != nullptr) { d.act2 = x1->d16; d.C2 = x1->C; d.taps2 = 1; }
