@@ -44,10 +44,13 @@ struct ConvGemmParams {
   int res_up;                  // epi_tma == 1 only: the residual is the nearest-2x upsample of a half-resolution tensor (TW == 16)
   int out16;                   // epi_tma == 1 only: also emit an fp16 copy of the output tile through maps.out16
   int epi_tma;                 // 1: fp32 NHWC output (+ residual) moved by TMA through swizzled smem tiles; 2: fp16 NHWC output
-  int slab_mode;               // kSlab kernel: 1 = three [18][8]-pixel slabs per chunk (one per horizontal shift, aligned descriptors);
-                               // 2 = ONE [18][16]-pixel slab per chunk, horizontal taps as descriptor starts 128 B apart inside a
-                               // swizzle atom (matrix base offset = dx; 3: same with base offset 0, to probe the hardware rule)
-  int fold;                    // kSlab mode 2 only: the GroupNorm affine + SiLU of the 3x3 segments is applied to the raw fp16 slab in shared
+  int slab_mode;               // kSlab kernel: 1 = three [18][8]-pixel slabs per chunk (one per horizontal shift, 1024-byte-aligned descriptor
+                               // starts); 2 = ONE [18][16]-pixel slab per chunk, horizontal taps as descriptor starts 128 B apart INSIDE
+                               // a swizzle atom; 3 = ONE [18][10]-pixel slab (pitch 10 rows of 128 B, 8-row groups 1280 B apart), three
+                               // slots.  Measured rule (profiles/slab_probe_r02w.json): the 128-byte swizzle of tcgen05.mma operands is a
+                               // function of the absolute shared-memory address, so unaligned starts need matrix base offset 0
+                               // (base offset = row offset gives wrong products)
+  int fold;                    // kSlab modes 2 / 3 only: the GroupNorm affine + SiLU of the 3x3 segments is applied to the raw fp16 slab in shared
                                // memory by the two spare warps (y = silu(A x + B), (A, B) per (sample, channel) from fold_ab; pixels
                                // outside the image stay zero), so the separate GroupNorm-apply pass of that operand disappears
   const float2* fold_ab;       // [N][fold_C]
@@ -99,8 +102,10 @@ struct ConvGemmCfg {
   static constexpr int SLAB_ROWS = 18;
   static constexpr int SLAB_A_BYTES = SLAB_ROWS * 8 * BK * 2;                  // 18 KB
   static constexpr int SLAB_SA = 3, SLAB_SB = 5;
-  // mode 2: [18 rows][16 px] slabs (36 KB), two of them, and a four-deep weight ring
+  // mode 2: [18 rows][16 px] slabs (36 KB), two of them, and a four-deep weight ring; mode 3: [18][10 px] slabs (22.5 KB in
+  // 23 KB slots), three of them
   static constexpr int SLAB2_A_BYTES = SLAB_ROWS * 16 * BK * 2, SLAB2_SA = 2, SLAB2_SB = 4;
+  static constexpr int SLAB3_A_BYTES = SLAB_ROWS * 10 * BK * 2, SLAB3_SLOT = ((SLAB3_A_BYTES + 1023) / 1024) * 1024, SLAB3_SA = 3;
   static constexpr int SLAB1_OPER = SLAB_SA * SLAB_A_BYTES + SLAB_SB * B_BYTES, SLAB2_OPER = SLAB2_SA * SLAB2_A_BYTES + SLAB2_SB * B_BYTES;
   static constexpr int SLAB_OPER_BYTES = SLAB1_OPER > SLAB2_OPER ? SLAB1_OPER : SLAB2_OPER;
   static constexpr int SMEM_BYTES_SLAB = SLAB_OPER_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;
@@ -244,9 +249,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t afull0 = mapa_cluster(smem_u32(&full_bar[0]), 0), bfull0 = mapa_cluster(smem_u32(&bfull_bar[0]), 0);
-      const bool wide = p.slab_mode >= 2;
-      const int na = wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
-      const int a_slot = wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      const bool wide = p.slab_mode >= 2, narrow = p.slab_mode == 3;
+      const int na = narrow ? Cfg::SLAB3_SA : wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
+      const int a_slot = narrow ? Cfg::SLAB3_SLOT : wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      const uint32_t a_bytes = narrow ? Cfg::SLAB3_A_BYTES : Cfg::SLAB2_A_BYTES;       // wide modes: bytes of one slab load
       uint8_t* b_ring = smem + na * a_slot;
       for (int w = w_first; w < w_limit; w += w_stride) {
         int mtp, colbase, ncols;
@@ -278,10 +284,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
             if (taps == 9 && wide) {
               mbar_wait(&empty_bar[sa], pa ^ 1);
               if (p.fold) {          // each CTA's slab lands on its own barrier; its transform warps release it to the MMA thread
-                mbar_arrive_expect_tx(&araw_bar[sa], Cfg::SLAB2_A_BYTES);
+                mbar_arrive_expect_tx(&araw_bar[sa], a_bytes);
                 tma_load_4d(&maps.a_mc[seg], &araw_bar[sa], smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
               } else {
-                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * Cfg::SLAB2_A_BYTES);
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2 * a_bytes);
                 tma_load_4d_2sm(&maps.a_mc[seg], afull0 + sa * 8, smem + sa * a_slot, ch * 64, w0 - 1, h0 - 1, n0);
               }
               if (++sa == na) { sa = 0; pa ^= 1; }
@@ -323,9 +329,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const bool wide = p.slab_mode >= 2;
-      const int na = wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
-      const int a_slot = wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      const bool wide = p.slab_mode >= 2, narrow = p.slab_mode == 3;
+      const int na = narrow ? Cfg::SLAB3_SA : wide ? Cfg::SLAB2_SA : Cfg::SLAB_SA, nb = wide ? Cfg::SLAB2_SB : Cfg::SLAB_SB;
+      const int a_slot = narrow ? Cfg::SLAB3_SLOT : wide ? Cfg::SLAB2_A_BYTES : Cfg::SLAB_A_BYTES;
+      const uint32_t row_pitch = narrow ? 10u * 128u : 16u * 128u;      // bytes between slab rows = between the 8-row groups of a tile
       const uint32_t b_ring = smem_u32(smem + na * a_slot);
       for (int w = w_first; w < w_limit; w += w_stride) {
         const uint32_t idesc = (w >= p.full_items) ? idesc_half : idesc_full;
@@ -361,12 +368,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
               tc_fence_after();
               const uint32_t a_addr = smem_u32(smem + sa * a_slot);
               if (taps == 9 && wide) {
-                // slab row (2048 B = 16 px) dy = image row y0 - 1 + dy; pixel column dx = image column x0 - 1 + dx: the tile row of
-                // tap (dy, dx) starts dx * 128 B into the swizzle atom of that slab row
+                // slab row dy = image row y0 - 1 + dy; pixel column dx = image column x0 - 1 + dx: the tile rows of tap (dy, dx)
+                // start (dy * pitch + dx) 128-byte rows into the slab; swizzle by absolute address, base offset 0
 #pragma unroll 1
                 for (int t = 0; t < 9; ++t) {
                   const uint32_t tdy = t / 3, tdx = t - 3 * tdy;
-                  tap(a_addr + tdy * 2048 + tdx * 128, 2048, p.slab_mode == 2 ? tdx : 0u);
+                  tap(a_addr + tdy * row_pitch + tdx * 128, row_pitch, 0u);
                 }
               } else if (taps == 9) {
 #pragma unroll 1
@@ -389,7 +396,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       if (p.fold) {
         const int tt = static_cast<int>(threadIdx.x) - 64;       // 0..63
         const int cq = tt & 7, pq = tt >> 3;                     // logical 16-byte channel chunk, pixel phase
-        const int na = Cfg::SLAB2_SA, a_slot = Cfg::SLAB2_A_BYTES;
+        const bool narrow = p.slab_mode == 3;
+        const int na = narrow ? Cfg::SLAB3_SA : Cfg::SLAB2_SA, a_slot = narrow ? Cfg::SLAB3_SLOT : Cfg::SLAB2_A_BYTES;
+        const int ppr = narrow ? 10 : 16;                        // 128-byte rows (pixels) per slab row
         int sa = 0;
         uint32_t pa = 0;
         const uint32_t ready0 = mapa_cluster(smem_u32(&full_bar[0]), 0);
@@ -422,14 +431,14 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
               mbar_wait(&araw_bar[sa], pa);
               if (xform) {
                 uint8_t* slab = smem + sa * a_slot;
-                // pixels (srow, px), px = 0..9 (image columns x0-1 .. x0+8), of the [18][16]-pixel slab; 128-byte rows, 16-byte
-                // chunks XOR-swizzled with the row index (TMA SWIZZLE_128B)
+                // pixels (srow, px), px = 0..9 (image columns x0-1 .. x0+8), of the [18][16 or 10]-pixel slab; 128-byte rows, 16-byte
+                // chunks XOR-swizzled with the row index (TMA SWIZZLE_128B, a function of the address: slots are 1024-byte aligned)
 #pragma unroll 2
                 for (int pp = pq; pp < Cfg::SLAB_ROWS * 10; pp += 8) {
                   const int srow = pp / 10, px = pp - srow * 10;
                   const int y = h0 - 1 + srow, x = w0 - 1 + px;
                   if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;        // conv zero padding stays zero
-                  const int r = srow * 16 + px;
+                  const int r = srow * ppr + px;
                   uint4* ptr = reinterpret_cast<uint4*>(slab + r * 128 + ((cq ^ (r & 7)) << 4));
                   const uint4 raw = *ptr;
                   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);

@@ -135,7 +135,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     if (l->BN == 256 && l->ctas == 1 && (pair_ok || d.out16 != nullptr)) l->BN = 128;
     // 3x3 tap reuse (conv_gemm_kernel<.., kSlab>): 8 x 16 pixel tiles; not with the upsampled residual (16-wide boxes)
     int slab_mode = getenv("IVID_SLAB") ? atoi(getenv("IVID_SLAB")) : 0;      // read per plan build (tests switch it)
-    if (d.fold_ab != nullptr) slab_mode = 2;
+    if (d.fold_ab != nullptr && slab_mode < 2) slab_mode = 3;      // fold: single-slab modes only (default: the 10-pixel pitch)
     if (slab_mode && l->ctas == 2 && d.taps0 == 9 && d.H >= 16 && d.W >= 16 && !d.residual_up) {
       l->slab = 1;
       p.slab_mode = slab_mode >= 2 ? slab_mode : 1;
@@ -144,7 +144,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
     }
     p.fold = 0; p.fold_ab = nullptr; p.fold_C = 0; p.fold_off[0] = p.fold_off[1] = p.fold_off[2] = -1;
     if (d.fold_ab != nullptr) {
-      IVID_REQUIRE(l->slab == 1 && p.slab_mode == 2, "conv: fold mode needs the CTA-pair tap-reuse kernel (see conv_fold_ok)");
+      IVID_REQUIRE(l->slab == 1 && p.slab_mode >= 2, "conv: fold mode needs the CTA-pair tap-reuse kernel (see conv_fold_ok)");
       IVID_REQUIRE(d.fold_C % 8 == 0 && d.fold_off0 % 8 == 0, "conv: fold coefficient table alignment");
       p.fold = 1; p.fold_ab = static_cast<const float2*>(d.fold_ab); p.fold_C = d.fold_C;
       p.fold_off[0] = d.fold_off0; p.fold_off[1] = d.C1 > 0 ? d.fold_off1 : -1; p.fold_off[2] = d.C2 > 0 ? d.fold_off2 : -1;
@@ -227,7 +227,7 @@ ConvLaunch* conv_launch_create(const ConvDesc& d) {
   }
   if (l->mc == 0) { M.a_mc[0] = M.a[0]; M.a_mc[1] = M.a[0]; M.a_mc[2] = M.a[0]; M.b_mc = M.b; }
   if (l->slab) {
-    const int sw = p.slab_mode >= 2 ? 16 : 8;        // slab width in pixels
+    const int sw = p.slab_mode == 3 ? 10 : p.slab_mode == 2 ? 16 : 8;        // slab width in pixels
     M.a_mc[0] = make_act_map(d.act0, d.N, d.H, d.W, d.C0, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
     if (d.C1 > 0 && d.taps1 == 9) M.a_mc[1] = make_act_map(d.act1, d.N, d.H, d.W, d.C1, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
     if (d.C2 > 0 && d.taps2 == 9) M.a_mc[2] = make_act_map(d.act2, d.N, d.H, d.W, d.C2, sw, ConvGemmCfg<256, 2>::SLAB_ROWS, 1);
