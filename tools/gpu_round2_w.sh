@@ -10,7 +10,7 @@ for v in "IVID_FOLD=0" "IVID_FOLD=1" "IVID_FOLD=1 IVID_SLAB=2" "IVID_FOLD=0" "IV
   python - <<PY
 import json
 try:
-    d=json.loads(open(""gpurun_out/bench_${TAG}_c2_${v// /_}.json"").read().strip().splitlines()[-1])
+    d=json.loads(open("gpurun_out/bench_${TAG}_c2_${v// /_}.json").read().strip().splitlines()[-1])
     f=d["roofline"]["families"]
     print("c2 ${v}: ms/step %.3f"%d["ms_per_step"], {k:(v["launches"], round(v["ms"],3)) for k,v in f.items() if k.startswith("conv") or k.startswith("gn")}, d["clocks"])
 except Exception as e:
