@@ -228,3 +228,22 @@ def test_backbone_options(tag):
         worst = max(worst, rt)
         print(f"[{tag}] {name} rel {rt:.3e}")
     assert worst < HARD_CAP
+
+
+def test_groupnorm_fold_matches_separate_apply(golden, monkeypatch):
+    """IVID_FOLD=1: on the CTA-pair 3x3 convs the GroupNorm affine + SiLU is applied to the raw fp16 slab inside the conv kernel
+    (gn_coeff_kernel + transform warps) instead of by a separate gn_apply pass.  Same operand bits by construction (same fmaf /
+    SiLU / fp16 rounding), so the eps of the two paths may only differ by the fp32 accumulation order of the tap-reuse kernel."""
+    cfg = json.loads(bytes(golden["schemacfg_rgbd_imagenet_adm_128_large_cfg"]).decode())
+    sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
+    g = torch.Generator().manual_seed(9)
+    N = 2
+    x = torch.randn(N, 4, 128, 128, generator=g).cuda(); t = torch.tensor([700, 20]).cuda(); c = torch.tensor([5, -1]).cuda()
+    monkeypatch.delenv("IVID_FOLD", raising=False)
+    base = _load(cfg, sd)(x, t, c).clone()
+    monkeypatch.setenv("IVID_FOLD", "1")
+    net = _load(cfg, sd)
+    got = net(x, t, c)
+    r = G.report("eps, GroupNorm fold vs separate apply", got, base.cpu())
+    assert r < 5e-5
+    assert torch.equal(net(x, t, c), got)          # and it is reproducible
