@@ -98,6 +98,7 @@ struct ConvGemmCfg {
   static constexpr int EPI_BYTES = 4 * EPI_PER_WARP;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + EPI_BYTES + 1024;   // +1024 alignment slack
   static constexpr int THREADS = 256;
+  static constexpr int THREADS_SLAB = 320;      // + warps 8, 9: with warps 2, 3 one operand-transform warp per scheduler (fold mode)
   // kSlab (3x3 tap reuse): activation ring of [18 rows][8 px][64 ch] slabs, weight ring of [BN / kCtas][64] tap tiles
   static constexpr int SLAB_ROWS = 18;
   static constexpr int SLAB_A_BYTES = SLAB_ROWS * 8 * BK * 2;                  // 18 KB
@@ -125,7 +126,7 @@ struct ConvGemmCfg {
 // row (1024 B = one 8-row swizzle atom) apart.  L2 -> shared-memory activation traffic per chunk: 3 x 18 KB instead of 9 x 16 KB;
 // with the nine 16 KB weight tiles (own ring) the operand traffic per FLOP drops by 1.45x.  maps.a_mc[] hold the slab boxes.
 template <int BN, int kCtas = 1, bool kMc = false, bool kSlab = false>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kSlab ? 320 : 256, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, kCtas>;
   constexpr int STAGES = Cfg::STAGES;
@@ -390,12 +391,12 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (kSlab && (warp == 2 || warp == 3)) {
+  } else if (kSlab && (warp == 2 || warp == 3 || warp >= 8)) {
     // ===================================== operand transform (fold mode): GroupNorm affine + SiLU in place =====================
     if constexpr (kSlab) {
       if (p.fold) {
-        const int tt = static_cast<int>(threadIdx.x) - 64;       // 0..63
-        const int cq = tt & 7, pq = tt >> 3;                     // logical 16-byte channel chunk, pixel phase
+        const int tt = warp < 4 ? static_cast<int>(threadIdx.x) - 64 : static_cast<int>(threadIdx.x) - 192;       // 0..127
+        const int cq = tt & 7, pq = tt >> 3;                     // logical 16-byte channel chunk, pixel phase (0..15)
         const bool narrow = p.slab_mode == 3;
         const int na = narrow ? Cfg::SLAB3_SA : Cfg::SLAB2_SA, a_slot = narrow ? Cfg::SLAB3_SLOT : Cfg::SLAB2_A_BYTES;
         const int ppr = narrow ? 10 : 16;                        // 128-byte rows (pixels) per slab row
@@ -433,8 +434,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
                 uint8_t* slab = smem + sa * a_slot;
                 // pixels (srow, px), px = 0..9 (image columns x0-1 .. x0+8), of the [18][16 or 10]-pixel slab; 128-byte rows, 16-byte
                 // chunks XOR-swizzled with the row index (TMA SWIZZLE_128B, a function of the address: slots are 1024-byte aligned)
-#pragma unroll 2
-                for (int pp = pq; pp < Cfg::SLAB_ROWS * 10; pp += 8) {
+#pragma unroll 4
+                for (int pp = pq; pp < Cfg::SLAB_ROWS * 10; pp += 16) {
                   const int srow = pp / 10, px = pp - srow * 10;
                   const int y = h0 - 1 + srow, x = w0 - 1 + px;
                   if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;        // conv zero padding stays zero
@@ -454,7 +455,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
                 }
                 fence_proxy_async_smem();      // the tensor core reads the slab through the async proxy
               }
-              asm volatile("bar.sync 2, 64;\n" ::: "memory");
+              asm volatile("bar.sync 2, 128;\n" ::: "memory");
               if (tt == 0) mbar_arrive_cluster(ready0 + sa * 8);
               if (++sa == na) { sa = 0; pa ^= 1; }
             }
@@ -558,7 +559,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) 
       if constexpr (kCtas == 2) tc_commit_2sm(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================================== epilogue =====================================
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // row of the 128-pixel tile

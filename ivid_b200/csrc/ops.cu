@@ -308,7 +308,7 @@ static void run_conv_pair(const ConvLaunch* l, cudaStream_t s) {
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(l->grid);
-  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.blockDim = dim3(l->slab ? Cfg::THREADS_SLAB : Cfg::THREADS);
   cfg.dynamicSmemBytes = l->slab ? Cfg::SMEM_BYTES_SLAB : Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
