@@ -245,5 +245,7 @@ def test_groupnorm_fold_matches_separate_apply(golden, monkeypatch):
     net = _load(cfg, sd)
     got = net(x, t, c)
     r = G.report("eps, GroupNorm fold vs separate apply", got, base.cpu())
-    assert r < 5e-5
+    assert r < NORTH_STAR
     assert torch.equal(net(x, t, c), got)          # and it is reproducible
+    ref = unet_ref.unet_forward(cfg, sd, x.cpu(), t.cpu(), c.cpu())
+    assert G.report("eps, GroupNorm fold vs oracle", got, ref) < HARD_CAP

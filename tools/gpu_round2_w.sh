@@ -1,20 +1,23 @@
 #!/bin/bash
-# Round-2 GPU batch Y: GroupNorm fold with four transform warps (320-thread tap-reuse kernel): parity + A/B.
+# Round-2 GPU batch Z (final): whole GPU suite, smoke, benches of the four configurations on the final build, fold diagnostic.
 mkdir -p gpurun_out
-TAG=${TAG:-r02y}
+TAG=${TAG:-r02z}
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -30 gpurun_out/build.log; }
-timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_ops.py -q -m gpu -x -k "fold or slab or (conv_matches and slab)" > gpurun_out/pytest_gpu_${TAG}_fold.log 2>&1; echo "== pytest fold/slab exit $?"; tail -3 gpurun_out/pytest_gpu_${TAG}_fold.log
-IVID_FOLD=1 timeout 900 python -m pytest tests/test_gpu_unet.py -q -m gpu -x -k "layerwise or three_timesteps" > gpurun_out/pytest_gpu_${TAG}_fold2.log 2>&1; echo "== pytest IVID_FOLD=1 exit $?"; tail -3 gpurun_out/pytest_gpu_${TAG}_fold2.log
-for v in "IVID_FOLD=0" "IVID_FOLD=1" "IVID_FOLD=0" "IVID_FOLD=1"; do
-  env $v timeout 600 python bench.py --config 2 --steps 20 --warmup 3 --no-cpu-baseline > "gpurun_out/bench_${TAG}_c2_${v}.json" 2>gpurun_out/bench_${TAG}.err
+timeout 1500 python -m pytest tests/ -q -m gpu > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "== pytest -m gpu exit $?"; tail -4 gpurun_out/pytest_gpu_${TAG}.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; echo "== smoke exit $?"; tail -2 gpurun_out/smoke_${TAG}.log
+timeout 600 python tools/micro/fold_diff.py 2> gpurun_out/fold_diff_${TAG}.err > gpurun_out/fold_diff_${TAG}.json; echo "== fold diff exit $?"; python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/fold_diff_${TAG}.json")); print("fold vs apply eps", d["eps_fold_vs_apply"], "fold vs fold", d["eps_fold_vs_fold"])
+    for b in d["blocks"][:14]: print(b)
+except Exception as e: print("parse failed", e)
+PY
+for c in 2 3 4 5; do
+  timeout 900 python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_c$c.json 2> gpurun_out/bench_${TAG}_c$c.err; echo "== bench c$c exit $?"
   python - <<PY
 import json
 try:
-    d=json.loads(open("gpurun_out/bench_${TAG}_c2_${v}.json").read().strip().splitlines()[-1])
-    f=d["roofline"]["families"]
-    print("c2 ${v}: ms/step %.3f"%d["ms_per_step"], {k:(v["launches"], round(v["ms"],3)) for k,v in f.items() if k.startswith("conv") or k.startswith("gn")}, d["clocks"])
-except Exception as e:
-    print("parse failed", e)
+    d=json.loads(open("gpurun_out/bench_${TAG}_c${c}.json").read().strip().splitlines()[-1]); print("c$c: value %.4f e2e %.4f ms/step %.2f"%(d["value"], d["e2e"]["value"], d["ms_per_step"]), d["clocks"])
+except Exception as e: print("parse failed", e)
 PY
 done
-tail -3 gpurun_out/bench_${TAG}.err
