@@ -233,7 +233,11 @@ def test_backbone_options(tag):
 def test_groupnorm_fold_matches_separate_apply(golden, monkeypatch):
     """IVID_FOLD=1: on the CTA-pair 3x3 convs the GroupNorm affine + SiLU is applied to the raw fp16 slab inside the conv kernel
     (gn_coeff_kernel + transform warps) instead of by a separate gn_apply pass.  Same operand bits by construction (same fmaf /
-    SiLU / fp16 rounding), so the eps of the two paths may only differ by the fp32 accumulation order of the tap-reuse kernel."""
+    SiLU / fp16 rounding); what differs is the fp32 accumulation order of the tap-reuse kernel (chunk-major instead of tap-major,
+    1e-6 relative), which flips ~0.1 % of the fp16 roundings of each hidden tensor: 1.9e-5 relative after the first ResBlock,
+    amplified by the network itself to 7.7e-4 at eps (tools/micro/fold_diff.py, measured per block) - the same sensitivity that
+    turns the per-layer fp16 noise into the 9e-4 distance from the fp32 oracle.  So the two paths are compared at the north-star
+    bar, each against the oracle at the hard cap, and the fold path must be bitwise reproducible."""
     cfg = json.loads(bytes(golden["schemacfg_rgbd_imagenet_adm_128_large_cfg"]).decode())
     sd = unet_ref.make_synthetic_state_dict(cfg, seed=1234)
     g = torch.Generator().manual_seed(9)
