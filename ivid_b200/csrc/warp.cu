@@ -180,16 +180,9 @@ __device__ __forceinline__ void rtri_make(const WVtx* v, int S, uint32_t prim, R
   r.valid = 1;
 }
 
-__device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis, int simple) {
-  const long long cx = static_cast<long long>(px) * 256 + 128, cy = static_cast<long long>(py) * 256 + 128;
-  long long E[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const long long e = r.ea[i] * cx + r.eb[i] * cy + r.ec[i];
-    if (e < 0 || (e == 0 && !((r.tie >> i) & 1))) return;
-    E[i] = e;
-  }
-  const float l0 = static_cast<float>(E[0]) / r.farea, l1 = static_cast<float>(E[1]) / r.farea, l2 = static_cast<float>(E[2]) / r.farea;
+// a covered pixel: depth, (aggregation mode) back-face padding discard, visibility key.  fE = the three edge values as floats
+__device__ __forceinline__ void rtri_cover(const RTri& r, float fE0, float fE1, float fE2, int px, int py, int S, unsigned long long* vis, int simple) {
+  const float l0 = fE0 / r.farea, l1 = fE1 / r.farea, l2 = fE2 / r.farea;
   const float z = (l0 * r.zw[0] + l1 * r.zw[1]) + l2 * r.zw[2];
   if (!(z > 0.f && z < 1.f)) return;
   if (!simple && !r.front) {
@@ -202,6 +195,42 @@ __device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S,
   atomicMin(vis + static_cast<size_t>(py) * S + px, key);
 }
 
+__device__ __forceinline__ void rtri_pixel(const RTri& r, int px, int py, int S, unsigned long long* vis, int simple) {
+  const long long cx = static_cast<long long>(px) * 256 + 128, cy = static_cast<long long>(py) * 256 + 128;
+  long long E[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const long long e = r.ea[i] * cx + r.eb[i] * cy + r.ec[i];
+    if (e < 0 || (e == 0 && !((r.tie >> i) & 1))) return;
+    E[i] = e;
+  }
+  rtri_cover(r, static_cast<float>(E[0]), static_cast<float>(E[1]), static_cast<float>(E[2]), px, py, S, vis, simple);
+}
+
+// Small bounding boxes (<= 48 pixels) of triangles whose edge coefficients fit 15 bits: the same exact integer edge functions,
+// evaluated once at the first pixel centre in 64 bits and then stepped in 32 bits (|E| < 2^31 inside the box: (|ea| + |eb|) <
+// 2^16 times at most 49 * 256 sub-pixels), one add per edge and pixel instead of two 64-bit multiply-adds.  float(int32 E) ==
+// float(int64 E) for the same integer, so the covered pixels get bit-identical barycentrics.
+__device__ __forceinline__ void rtri_scan_small32(const RTri& r, int S, unsigned long long* vis, int simple) {
+  const long long cx0 = static_cast<long long>(r.px0) * 256 + 128, cy0 = static_cast<long long>(r.py0) * 256 + 128;
+  int erow[3], sx[3], sy[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    erow[i] = static_cast<int>(r.ea[i] * cx0 + r.eb[i] * cy0 + r.ec[i]);
+    sx[i] = static_cast<int>(r.ea[i]) * 256;
+    sy[i] = static_cast<int>(r.eb[i]) * 256;
+  }
+  for (int py = r.py0; py <= r.py1; ++py) {
+    int e0 = erow[0], e1 = erow[1], e2 = erow[2];
+    for (int px = r.px0; px <= r.px1; ++px) {
+      const bool in0 = e0 > 0 || (e0 == 0 && (r.tie & 1)), in1 = e1 > 0 || (e1 == 0 && (r.tie & 2)), in2 = e2 > 0 || (e2 == 0 && (r.tie & 4));
+      if (in0 && in1 && in2) rtri_cover(r, static_cast<float>(e0), static_cast<float>(e1), static_cast<float>(e2), px, py, S, vis, simple);
+      e0 += sx[0]; e1 += sx[1]; e2 += sx[2];
+    }
+    erow[0] += sy[0]; erow[1] += sy[1]; erow[2] += sy[2];
+  }
+}
+
 // Small triangles (the common 3x3-pixel case) are scanned by their own lane; triangles with a large bounding box (the
 // frustum ring and faces stretched across depth discontinuities) are broadcast to the warp and scanned by all 32 lanes.
 // `stash` = this warp's 32 rows of a shared-memory table: a lane parks its big triangle there and the warp reads the leader's row
@@ -212,8 +241,23 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
   const int w = r.valid ? (r.px1 - r.px0 + 1) : 0, h = r.valid ? (r.py1 - r.py0 + 1) : 0;
   const bool big = r.valid && (w * h > kSmall);
   if (r.valid && !big) {
-    for (int py = r.py0; py <= r.py1; ++py)
-      for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis, simple);
+    bool fit = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fit = fit && r.ea[i] > -32768 && r.ea[i] < 32768 && r.eb[i] > -32768 && r.eb[i] < 32768;
+    // the first-pixel edge values must also fit 31 bits (they do whenever the box lies within ~2^15 sub-pixels of the triangle,
+    // i.e. always for on-screen boxes of such triangles; checked, not assumed)
+    const long long cx0 = static_cast<long long>(r.px0) * 256 + 128, cy0 = static_cast<long long>(r.py0) * 256 + 128;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long e = r.ea[i] * cx0 + r.eb[i] * cy0 + r.ec[i];
+      fit = fit && e > -(1ll << 29) && e < (1ll << 29);
+    }
+    if (fit) {
+      rtri_scan_small32(r, S, vis, simple);
+    } else {
+      for (int py = r.py0; py <= r.py1; ++py)
+        for (int px = r.px0; px <= r.px1; ++px) rtri_pixel(r, px, py, S, vis, simple);
+    }
   }
   unsigned mask = __ballot_sync(0xffffffffu, big);
   if (mask == 0u) return;
