@@ -308,10 +308,24 @@ __device__ __forceinline__ void rtri_raster(RTri& r, int S, unsigned long long* 
         km &= km - 1;
         const int stx = __shfl_sync(0xffffffffu, tx, sl), sty = __shfl_sync(0xffffffffu, ty, sl);
         const int x0 = max(stx * 8, b.px0), x1 = min(stx * 8 + 7, b.px1), y0 = max(sty * 8, b.py0), y1 = min(sty * 8 + 7, b.py1);
+        // a lane owns pixel (lane & 7, lane >> 3) of the tile and the one four rows below: the edge values of the first are
+        // evaluated (three 64-bit multiply-adds), those of the second follow by adding 4 * 256 * eb (same exact integers)
+        {
+          const int px = stx * 8 + (lane & 7), py = sty * 8 + (lane >> 3);
+          const long long cx = static_cast<long long>(px) * 256 + 128, cy = static_cast<long long>(py) * 256 + 128;
+          long long E[3];
 #pragma unroll
-        for (int idx = lane; idx < 64; idx += 32) {
-          const int px = stx * 8 + (idx & 7), py = sty * 8 + (idx >> 3);
-          if (px >= x0 && px <= x1 && py >= y0 && py <= y1) rtri_pixel(b, px, py, S, vis, simple);
+          for (int i = 0; i < 3; ++i) E[i] = b.ea[i] * cx + b.eb[i] * cy + b.ec[i];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int qy = py + 4 * half;
+            bool in = px >= x0 && px <= x1 && qy >= y0 && qy <= y1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) in = in && (E[i] > 0 || (E[i] == 0 && ((b.tie >> i) & 1)));
+            if (in) rtri_cover(b, static_cast<float>(E[0]), static_cast<float>(E[1]), static_cast<float>(E[2]), px, qy, S, vis, simple);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) E[i] += b.eb[i] * 1024;
+          }
         }
       }
     }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU batch AA: 32-bit incremental edge stepping in the rasteriser's small-triangle path: bit-exact tests + timing.
 mkdir -p gpurun_out
-TAG=${TAG:-r02aa}
+TAG=${TAG:-r02ab}
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -30 gpurun_out/build.log; }
 timeout 900 python -m pytest tests/test_gpu_warp.py tests/test_gpu_pipeline.py -q -m gpu -x > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "== pytest warp+pipeline exit $?"; tail -3 gpurun_out/pytest_gpu_${TAG}.log
 for i in 1 2; do
