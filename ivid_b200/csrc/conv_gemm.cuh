@@ -125,6 +125,11 @@ struct ConvGemmCfg {
 // image) and the three vertical taps of a slab are the same shared-memory bytes read through descriptors that start one slab
 // row (1024 B = one 8-row swizzle atom) apart.  L2 -> shared-memory activation traffic per chunk: 3 x 18 KB instead of 9 x 16 KB;
 // with the nine 16 KB weight tiles (own ring) the operand traffic per FLOP drops by 1.45x.  maps.a_mc[] hold the slab boxes.
+// Modes 2 / 3 (ConvGemmParams::slab_mode) load ONE slab per chunk ([18][16] or [18][10] pixels) and read the horizontal taps
+// through descriptor starts 128 B apart inside a swizzle atom (swizzle by absolute address: matrix base offset 0).  On those,
+// fold mode (ConvGemmParams::fold) lets warps 2, 3, 8, 9 (the kernel then runs 320 threads) apply the GroupNorm affine + SiLU
+// to the raw slab in place between the TMA barrier and the MMA's "operand ready" barrier.  All of it is opt-in (IVID_SLAB,
+// IVID_FOLD): measured slower than the tap-by-tap kernel + separate GroupNorm pass.
 template <int BN, int kCtas = 1, bool kMc = false, bool kSlab = false>
 __global__ void __launch_bounds__(kSlab ? 320 : 256, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvGemmParams p) {
